@@ -1,0 +1,119 @@
+"""CPU: the oracle (oracle/qa_oracle.py) against the golden fixtures made from the reference."""
+import numpy as np
+import pytest
+
+from oracle import qa_oracle as orc
+from tests import golden_util as G
+
+
+@pytest.mark.parametrize("name", G.kat_cases())
+def test_formats_bit_exact(name):
+    x, outs = G.kat(name)
+    with np.errstate(all="ignore"):
+        for fmt in G.FORMATS:
+            got = G.bits(orc.quantize(x, fmt))
+            assert np.array_equal(got, outs[fmt]), f"{name}/{fmt}"
+
+
+def test_appendix_c_hex_vectors():
+    # SURVEY.md Appendix C, bfp4 row of the 16-element known-answer group
+    x, outs = G.kat("appendix_c_row")
+    want = "3f800000 3f800000 3f800000 3f000000 3f000000 bf400000 00000000 00000000 bfe00000 3fe00000 " \
+           "00000000 00000000 00000000 3e800000 be800000 00000000"
+    assert [f"{v:08x}" for v in outs["bfp4"]] == want.split()
+    assert [f"{v:08x}" for v in G.bits(orc.quantize(x, "bfp4"))] == want.split()
+
+
+def test_numpy_arith_restatements_match_numpy():
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((50, 1024)).astype(np.float32)
+    b = (a + rng.standard_normal((50, 1024)).astype(np.float32) * 0.01).astype(np.float32)
+    assert np.array_equal(orc.np_pairwise_sum(a), np.add.reduce(a, axis=1))
+    for n in (7, 100, 130, 1000):
+        v = rng.standard_normal((3, n)).astype(np.float32)
+        assert np.array_equal(orc.np_pairwise_sum(v), np.add.reduce(v, axis=1))
+    d64 = a.astype(np.float64) * 1e3
+    assert np.array_equal(orc.np_pairwise_sum(d64), np.add.reduce(d64, axis=1))
+    from threadpoolctl import threadpool_info
+    arch = {d.get("architecture") for d in threadpool_info() if d.get("internal_api") == "openblas"}
+    if arch and arch != {"SkylakeX"}:
+        pytest.skip(f"np.dot uses a different OpenBLAS kernel here: {arch}")
+    want = np.array([np.dot(a[i], b[i]) for i in range(a.shape[0])], dtype=np.float32)
+    assert np.array_equal(orc.np_sdot_f32(a, b), want)
+    rows = orc.pearson_f32_rows(a, b)
+    want = np.array([orc.pearson_f32(a[i], b[i]) for i in range(a.shape[0])], dtype=np.float32)
+    assert np.array_equal(rows, want)
+
+
+@pytest.mark.parametrize("name", G.algo_case_names())
+def test_tile_scores_bit_exact(name):
+    x = G.algo_input(name)
+    z = G.npz("algo_small.npz")
+    for metric in ("pcc", "mae", "atol"):
+        sc = orc.padded_tile_scores(x, G.MIXED, metric)
+        for fmt in G.MIXED:
+            want = z[f"{name}__tilescore__{fmt}__{metric}"]
+            assert np.array_equal(sc[fmt].view(np.uint32), want.view(np.uint32)), (name, fmt, metric)
+
+
+def _formats_for(params):
+    raw = params.get("formats")
+    if raw:
+        return [p.strip() for p in raw.split(",")]
+    return list(G.MIXED)
+
+
+@pytest.mark.parametrize("name", G.algo_case_names())
+def test_algorithms_match_reference(name):
+    x = G.algo_input(name)
+    table = orc.tile_stat_table(x)
+    for key, m, want_assign, want_y in G.algo_runs(name):
+        p, fmts = m["params"], _formats_for(m["params"])
+        if m["algo"] == "mixed-tile-greedy":
+            a, counts = orc.greedy_assign(table, fmts, p["metric"], p["threshold"], p["seed"])
+        elif m["algo"] == "mixed-tile-threshold":
+            sc = orc.padded_tile_scores(x, fmts, p["metric"])
+            a, counts = orc.threshold_assign(sc, fmts, p["metric"], p["threshold"], table["th"], table["tw"])
+        else:
+            a, counts, samples = orc.random_assign(x, fmts, p["metric"], p["threshold"], p["iters"], p["seed"])
+            for s, w in zip(samples, m["samples"]):
+                assert s["counts"] == w["counts"] and s["total_bytes"] == w["total_bytes"]
+                assert s["pcc"] == w["pcc"] and s["mae"] == w["mae"] and s["atol"] == w["atol"]
+        assert np.array_equal(a, want_assign), key
+        assert counts == m["counts"], key
+        assert orc.total_bytes(counts) == m["tile_bytes"], key
+        y = orc.apply_assignment(x, a)
+        assert np.array_equal(G.bits(y), want_y.reshape(-1)), key
+
+
+def test_cfg1_shape_goldens():
+    from quantization_analysis_b200 import synthetic
+    import hashlib
+    meta, z = G.js("cfg1_q_a_proj.json"), G.npz("cfg1_q_a_proj.npz")
+    x = synthetic.randn_f32_np((1536, 7168), 0)
+    assert hashlib.sha256(x.tobytes()).hexdigest() == meta["input_sha256"]
+    for fmt in G.FORMATS:
+        y = orc.quantize(x, fmt)
+        assert hashlib.sha256(y.tobytes()).hexdigest() == meta["none"][fmt]["y_sha256"]
+        ex = orc.exact_metrics_f64(x, y)
+        # the reference's float32 pcc is only ~1e-5 accurate; mae/atol are tight
+        assert abs(ex["pcc"] - meta["none"][fmt]["pcc_f32"]) < 5e-5
+        assert ex["mae"] == pytest.approx(meta["none"][fmt]["mae_f32"], rel=2e-6, abs=0)
+        assert ex["atol"] == meta["none"][fmt]["atol_f32"]
+    table = orc.tile_stat_table(x)
+    a, counts = orc.greedy_assign(table, G.MIXED, "pcc", 0.999, 123)
+    assert np.array_equal(a, z["greedy_pcc0999_seed123"])
+    assert counts == meta["greedy_pcc0999_seed123"]["counts"]
+
+
+def test_pcg64_restatement_matches_numpy_streams():
+    z = G.npz("numpy_rng.npz")
+    r = orc.Pcg64(123)
+    assert np.array_equal(r.permutation(10752), z["s123__perm_10752"])
+    assert np.array_equal(r.permutation(777), z["s123__perm_777"])
+    assert np.array_equal(r.integers(4, 1000), z["s123__int4_1000"])
+    assert np.array_equal(r.integers(3, 1000), z["s123__int3_1000"])
+    assert np.array_equal(r.permutation(4096), z["s123__perm_4096"])
+    assert np.array_equal(r.integers(2, 777), z["s123__int2_777"])
+    assert np.array_equal(r.permutation(2), z["s123__perm_2"])
+    assert np.array_equal(r.permutation(1), z["s123__perm_1"])
