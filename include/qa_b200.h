@@ -1,0 +1,146 @@
+/* qa_b200.h — C ABI of the B200-native quantize-and-score library (libqa_b200.so).
+ *
+ * The reference (johanna-rock/quantization_analysis) is pure Python/NumPy and has no FFI of
+ * its own; each entry point below names the reference function(s) whose inner loop it
+ * replaces (paths relative to the reference root).  The Python host side in
+ * quantization_analysis_b200/ binds these with ctypes and keeps the reference's API.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates); no hidden
+ *    allocations, no implicit synchronisation; work is enqueued on `stream` (a cudaStream_t).
+ *  - return value 0 = ok, non-zero = error; qa_last_error() returns a thread-local message.
+ *  - the small index arrays fmt_order / order / fmt_indices are HOST pointers (copied by value).
+ *  - matrices are row-major [rows, cols] with leading dimension `ld` (elements).
+ *  - x_dtype: QA_DT_BF16 = raw bf16 bit patterns (uint16), QA_DT_F32 = float32.
+ *  - formats are numbered in the reference's MIXED_TILE_FORMATS order
+ *    (compression_algorithms/tile_utils.py:8): 0 bf16, 1 bfp8, 2 bfp4, 3 bfp2; fmt_mask bit i
+ *    selects format i.  fp0 (all zeros) needs no kernel.
+ *  - tiles are 32x32, numbered row-major: tile = tr * tiles_w + tc, tiles_w = ceil(cols/32).
+ */
+#ifndef QA_B200_H
+#define QA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QA_DT_BF16 0
+#define QA_DT_F32 1
+
+#define QA_METRIC_PCC 0
+#define QA_METRIC_MAE 1
+#define QA_METRIC_ATOL 2
+
+#define QA_NFMT 4
+/* tile-stat table: QA_NSTAT float64 columns, column-major: table[stat * ntiles + tile] */
+#define QA_NSTAT 22
+#define QA_STAT_SX 0  /* sum x            */
+#define QA_STAT_SX2 1 /* sum x*x          */
+/* for format f: base = 2 + 5*f; +0 sum y, +1 sum y*y, +2 sum x*y, +3 sum |x-y|, +4 max |x-y| */
+#define QA_STAT_FMT(f, k) (2 + 5 * (f) + (k))
+
+#define QA_STATS_FAST 0   /* bf16 input only; exact group-scaled partial sums               */
+#define QA_STATS_STRICT 1 /* NumPy-order float64 pairwise sums (bit-faithful to the reference) */
+
+/* State of a numpy.random.Generator(PCG64) (bit_generator.state), resident in device memory.
+ * Kernels advance it in place so successive calls continue the same stream. */
+typedef struct qa_pcg64 {
+    uint64_t state_hi, state_lo; /* 128-bit LCG state   */
+    uint64_t inc_hi, inc_lo;     /* 128-bit increment   */
+    uint32_t has_uint32;         /* buffered upper half */
+    uint32_t uinteger;
+} qa_pcg64;
+
+typedef void* qa_stream_t; /* cudaStream_t */
+
+int qa_version(void);
+const char* qa_last_error(void);
+
+/* Quantize->dequantize emulation for the selected formats, bit-exact, in one pass over x.
+ * Replaces quantization_formats.py:84-164 (quantize_dequantize_bfp_ttnn) and :29-45 (bf16 RNE)
+ * as called through quantize_weight_values (:171-194) / Quantizer.quantize (quantizer.py:13-34).
+ * out[f] (f in fmt_mask) receives rows*cols bf16 bit patterns, contiguous (ld = cols): every
+ * reconstruction has <= 7 explicit mantissa bits, so bf16 holds it exactly. */
+int qa_quant_recon(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                   uint32_t fmt_mask, void* const out[QA_NFMT], qa_stream_t stream);
+
+/* Fused quantize + per-tile reconstruction-error statistics (one read of x).
+ * Replaces the per-tile sums of mixed_tile_greedy.py:135-220,245-254 and feeds the tensor-level
+ * metrics of wq:684-687 / mixed_tile_random.py:135-141.  vec_tail: 0, or for a 1-D input laid
+ * out as rows of 32 (tile_utils.py:96-102) the number of valid elements in the last row (strict
+ * mode sums that ragged row as its own view, mixed_tile_greedy.py:111-131).
+ * Only the columns of formats in fmt_mask (and SX/SX2) are written. */
+int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                  int64_t vec_tail, uint32_t fmt_mask, int mode, double* table,
+                  qa_stream_t stream);
+
+/* NumPy-float32-faithful per-tile scores on zero-padded 32x32 tiles.
+ * Replaces tile_utils.py:46-57 (tile_metrics) incl. metrics.py:6-16 (pearson_corr) with the
+ * float32 summation orders of NumPy 2.3.5 / OpenBLAS 0.3.30 SkylakeX.
+ * scores[(metric * QA_NFMT + f) * ntiles + tile], float32, for all three metrics. */
+int qa_tile_scores_f32(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                       uint32_t fmt_mask, float* scores, qa_stream_t stream);
+
+/* numpy.random.Generator.permutation(n) / .integers(0, k, n) continued from *rng on device
+ * (mixed_tile_greedy.py:225,231; mixed_tile_random.py:116,133).  out_perm: int32[n];
+ * out_vals: int8[n].  work: int32[2*n] scratch for the permutation. */
+int qa_numpy_permutation(qa_pcg64* rng, int64_t n, int32_t* out_perm, int32_t* work,
+                         qa_stream_t stream);
+int qa_numpy_integers(qa_pcg64* rng, int k, int64_t n, int8_t* out_vals, qa_stream_t stream);
+
+/* Greedy per-tile format assignment under a global metric constraint.
+ * Replaces MixedTileGreedyCompression._compress, mixed_tile_greedy.py:135-346, driven by the
+ * tile-stat table.  fmt_order[nfmt] = candidate formats (first = base).  numel = element count
+ * of the original tensor.  Outputs: assignment int8[ntiles]; counts int64[QA_NFMT];
+ * state double[8] = final {sx, sx2, sy, sy2, sxy, sabs, max_abs, value}.
+ * work: at least qa_greedy_work_bytes(ntiles) bytes. */
+int64_t qa_greedy_work_bytes(int64_t ntiles);
+int qa_greedy_assign(const double* table, int64_t ntiles, double numel, int metric,
+                     double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
+                     int8_t* assignment, int64_t* counts, double* state, void* work,
+                     qa_stream_t stream);
+
+/* Per-tile threshold assignment for nthr thresholds at once.
+ * Replaces mixed_tile_threshold.py:111-123 and scripts/sweep_mixed_tile_threshold.py:145-155.
+ * scores: float32[QA_NFMT][ntiles] of ONE metric; order[norder]: formats by ascending bytes;
+ * a tile takes the first format whose float32 score passes (>= for pcc, <= otherwise) the
+ * float32 threshold, else order[norder-1].  assignment int8[nthr][ntiles],
+ * counts int64[nthr][QA_NFMT]. */
+int qa_threshold_assign(const float* scores, int64_t ntiles, const int32_t* order, int norder,
+                        int is_pcc, const float* thresholds, int nthr, int8_t* assignment,
+                        int64_t* counts, qa_stream_t stream);
+
+/* Random-assignment search: `iters` uniform assignments drawn from the NumPy stream, each scored
+ * from the table (float64 recombination).  Replaces mixed_tile_random.py:132-155.
+ * fmt_indices[nfmt]: candidate formats.  sample_metrics double[iters][3] = pcc, mae, atol;
+ * sample_counts int64[iters][QA_NFMT].  choices: int8[iters][ntiles] (format index per tile)
+ * must be pre-filled when `choices_ready` != 0 (k not a power of two), else it is produced
+ * here by jumping the PCG64 stream; *rng is advanced past iters*ntiles draws. */
+int qa_random_samples(const double* table, int64_t ntiles, double numel,
+                      const int32_t* fmt_indices, int nfmt, int iters, qa_pcg64* rng,
+                      int8_t* choices, int choices_ready, double* sample_metrics,
+                      int64_t* sample_counts, qa_stream_t stream);
+
+/* Apply a tile assignment: out = per-tile reconstruction in the assigned format (bf16 bits).
+ * Replaces the gather of mixed_tile_threshold.py:125-130 / mixed_tile_random.py:74-86 and
+ * scripts/reconstruct_mixed_tile_assignment.py:82-137.  assignment < 0 copies x (bf16-rounded). */
+int qa_apply_assignment(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                        const int8_t* assignment, void* out_bf16, qa_stream_t stream);
+
+/* Whole-tensor sums for a given assignment (or a single format when assignment == NULL and
+ * fmt >= 0), reduced from the table in a fixed order: out double[8] =
+ * {sx, sx2, sy, sy2, sxy, sabs, max_abs, 0}.  Feeds wq:684-687-style scoring. */
+int qa_assignment_sums(const double* table, int64_t ntiles, const int8_t* assignment, int fmt,
+                       double* out, qa_stream_t stream);
+
+/* fp32 -> bf16 bit patterns plus a count of elements that are NOT bf16-exact (low 16 bits != 0).
+ * Host helper for the numpy-in API.  inexact_count: uint64 on device (accumulated). */
+int qa_f32_to_bf16_checked(const float* x, int64_t n, void* out_bf16, unsigned long long* inexact_count,
+                           qa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QA_B200_H */

@@ -1,0 +1,71 @@
+"""mixed-tile-greedy on the device (reference: compression_algorithms/mixed_tile_greedy.py:20-378).
+
+One fused pass builds the per-tile statistic table (qa_tile_stats); the greedy decision chain -
+NumPy-stream permutation per candidate format, accept a tile's switch iff the global metric
+recomputed from running float64 sums still passes - runs on the device over that table
+(qa_greedy_assign); the final reconstruction is a per-tile apply (qa_apply_assignment).
+"""
+from __future__ import annotations
+
+import secrets
+
+from .. import engine
+from .base import CompressionAlgorithm, CompressionResult
+from . import _mixed_common as mc
+from .tile_utils import MIXED_TILE_FORMATS
+
+
+class MixedTileGreedyCompression(CompressionAlgorithm):
+    name = "mixed-tile-greedy"
+
+    def __init__(self, params: dict | None = None) -> None:
+        super().__init__(params=params)
+        raw = self.params.get("formats", self.params.get("tile_formats"))
+        self.metric = self.params.get("metric", "pcc")
+        self.threshold = float(self.params.get("threshold", 0.999))
+        self.seed = int(self.params.get("seed", 0))
+        self.strict = bool(self.params.get("strict_sums", False))   # extension: NumPy-order float64 tile sums
+        self.tile_formats = mc.parse_formats(raw) if raw is not None else None
+        if self.metric not in mc.VALID_METRICS:
+            raise ValueError(f"Unsupported metric: {self.metric}")
+
+    @classmethod
+    def from_params(cls, params: dict | None = None) -> "MixedTileGreedyCompression":
+        return cls(params=params or {})
+
+    def expected_evals(self, formats) -> int:
+        return 1
+
+    _parse_formats = staticmethod(mc.parse_formats)
+
+    @staticmethod
+    def _filter_from_formats(formats):
+        return mc.filter_formats(formats, "mixed-tile-greedy")
+
+    def run_prepared(self, p: engine.Prepared, tile_formats, table=None, seed: int | None = None) -> mc.DeviceResult:
+        """Device-resident run; `table` may be shared between algorithms on the same tensor."""
+        if table is None:
+            table = engine.tile_stats(p, MIXED_TILE_FORMATS, strict=True if self.strict else None)
+        seed = self.seed if seed is None else seed
+        if seed == 0:
+            seed = secrets.randbits(31)           # mixed_tile_greedy.py:222-224
+        rng = engine.make_rng(seed, p.data.device)
+        assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng)
+        counts = mc.counts_dict(counts_dev)
+        sums = engine.assignment_sums(table, assignment)
+        metrics = engine.metrics_from_sums(sums.cpu().numpy(), p.numel)
+        return mc.DeviceResult(self.name, p, assignment, counts, mc.total_bytes(counts), metrics, list(tile_formats),
+                               meta={"seed": seed, "state": state, "table": table})
+
+    def _compress(self, xf, quantizer, tile_formats):
+        if mc.numel_of(xf) == 0:
+            return mc.empty_result(xf)
+        dr = self.run_prepared(engine.prepare_tiles(xf), tile_formats)
+        return mc.finish(dr, xf)
+
+    def run(self, xf, formats, quantizer=None, cache=None):
+        tile_formats = self.tile_formats or self._filter_from_formats(formats)
+        y, counts, assignment = self._compress(xf=xf, quantizer=quantizer, tile_formats=tile_formats)
+        return [CompressionResult(fmt="MIXED", compression=self.name, y=y, tile_counts=counts,
+                                  tile_bytes=mc.total_bytes(counts),
+                                  meta={"assignment": assignment, "tile_formats": tile_formats})]

@@ -1,0 +1,422 @@
+// Fused quantize + per-tile statistics.
+//
+// FAST kernel (bf16 input).  A lane owns one 16-element shared-exponent group per row (one
+// 256-bit load) and walks the 32 rows of a tile stripe; lanes (2j, 2j+1) together cover tile j of
+// the warp's 512-column chunk.  All per-element arithmetic runs in "group units": the group is
+// scaled by the exact power of two 2^(134-E) so that every value is a small dyadic number,
+//   X = x * 2^(134-E)               |X| <= 255
+//   y_f = clamp(rne(X, step_f))     via the (X + 1.5*2^23*step) - 1.5*2^23*step trick, exact
+//   r_f = X - y_f                   exact
+// and the in-group float32 partial sums  sum y, sum y^2, sum r*y, sum |r|, sum r8, sum r8^2  are
+// exact (bounded integers / short dyadics; see DESIGN.md for the bit budget).  Once per group the
+// partials are widened to float64 and scaled by 2^(E-134) or its square, so the per-tile float64
+// sums are exact whenever they are representable - which is also when NumPy's pairwise float64
+// sums in the reference are exact, making the two bit-identical in that (normal) case.
+//   sum x   = (sum y8 + sum r8) * s         sum x^2 = (sum y8^2 + 2 sum r8 y8 + sum r8^2) * s^2
+//   sum x y = (sum y^2 + sum r y) * s^2
+//
+// STRICT kernel (bf16 or fp32 input).  One warp per tile; float32 products and float64 sums in
+// NumPy's pairwise order over the flattened valid view(s) of the tile, i.e. the same roundings
+// as np.sum(..., dtype=np.float64) in mixed_tile_greedy.py:147-174.
+#include "qa_common.cuh"
+
+namespace qa {
+
+// ------------------------------------------------------------------------------------------
+// FAST
+// ------------------------------------------------------------------------------------------
+struct TileAcc {
+    double sx, sx2;
+    double sy[3], sy2[3], sxy[3], sab[3];
+    float amax[3];
+};
+
+__device__ __forceinline__ void acc_zero(TileAcc& a) {
+    a.sx = a.sx2 = 0.0;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) { a.sy[f] = a.sy2[f] = a.sxy[f] = a.sab[f] = 0.0; a.amax[f] = 0.f; }
+}
+
+// Generic (any exponent, inf/nan, tiny E) fallback: integer quantizer + direct f64 accumulation.
+__device__ __noinline__ void group_slow(const uint32_t (&w)[8], uint32_t E, TileAcc& a) {
+#pragma unroll 1
+    for (int i = 0; i < GROUP; ++i) {
+        const uint32_t u = (i & 1) ? (w[i >> 1] & 0xFFFF0000u) : (w[i >> 1] << 16);
+        const float x = __uint_as_float(u);
+        a.sx += (double)x;
+        a.sx2 += (double)__fmul_rn(x, x);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const uint32_t yb = f == 0 ? bfp_recon_bits<7>(u, E) : f == 1 ? bfp_recon_bits<3>(u, E) : bfp_recon_bits<1>(u, E);
+            const float y = __uint_as_float(yb);
+            const float r = fabsf(__fsub_rn(x, y));
+            a.sy[f] += (double)y;
+            a.sy2[f] += (double)__fmul_rn(y, y);
+            a.sxy[f] += (double)__fmul_rn(x, y);
+            a.sab[f] += (double)r;
+            a.amax[f] = fmaxf(a.amax[f], r);
+        }
+    }
+}
+
+template <int F>
+struct Fmt;
+template <> struct Fmt<0> { static constexpr float M = 25165824.f, L = 254.f; };     // bfp8: step 2
+template <> struct Fmt<1> { static constexpr float M = 402653184.f, L = 224.f; };    // bfp4: step 32
+template <> struct Fmt<2> { static constexpr float M = 1610612736.f, L = 128.f; };   // bfp2: step 128
+
+__device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
+    // shared exponent: max of |bf16| patterns, two per word
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t v = w[i] & 0x7FFF7FFFu;
+        asm("max.u16x2 %0, %1, %2;" : "=r"(m) : "r"(m), "r"(v));
+    }
+    const uint32_t E = max(m & 0xFFFFu, m >> 16) >> 7;
+    if (E == 0u) return;                         // every element is zero/denormal: flushed (x ~ 0)
+    if (E < 24u || E == 255u) { group_slow(w, E, a); return; }
+
+    const float inv = __uint_as_float((261u - E) << 23);  // 2^(134-E)
+    float sy[3] = {0.f, 0.f, 0.f}, sy2[3] = {0.f, 0.f, 0.f}, sry[3] = {0.f, 0.f, 0.f}, sab[3] = {0.f, 0.f, 0.f},
+          mx[3] = {0.f, 0.f, 0.f};
+    float sr8 = 0.f, sr8q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float x = __uint_as_float(h ? (w[i] & 0xFFFF0000u) : (w[i] << 16));
+            const float X = x * inv;
+            {
+                float y = (X + Fmt<0>::M) - Fmt<0>::M;
+                y = fminf(fmaxf(y, -Fmt<0>::L), Fmt<0>::L);
+                const float r = X - y;
+                sy[0] += y; sy2[0] = fmaf(y, y, sy2[0]); sry[0] = fmaf(r, y, sry[0]);
+                sab[0] += fabsf(r); mx[0] = fmaxf(mx[0], fabsf(r));
+                sr8 += r; sr8q = fmaf(r, r, sr8q);
+            }
+            {
+                float y = (X + Fmt<1>::M) - Fmt<1>::M;
+                y = fminf(fmaxf(y, -Fmt<1>::L), Fmt<1>::L);
+                const float r = X - y;
+                sy[1] += y; sy2[1] = fmaf(y, y, sy2[1]); sry[1] = fmaf(r, y, sry[1]);
+                sab[1] += fabsf(r); mx[1] = fmaxf(mx[1], fabsf(r));
+            }
+            {
+                float y = (X + Fmt<2>::M) - Fmt<2>::M;
+                y = fminf(fmaxf(y, -Fmt<2>::L), Fmt<2>::L);
+                const float r = X - y;
+                sy[2] += y; sy2[2] = fmaf(y, y, sy2[2]); sry[2] = fmaf(r, y, sry[2]);
+                sab[2] += fabsf(r); mx[2] = fmaxf(mx[2], fabsf(r));
+            }
+        }
+    }
+    const double s1 = __hiloint2double((int)((E + 889u) << 20), 0);        // 2^(E-134)
+    const double s2 = __hiloint2double((int)((2u * E + 755u) << 20), 0);   // 2^(2E-268)
+    const float s1f = __uint_as_float((E - 7u) << 23);
+    a.sx = fma((double)sy[0] + (double)sr8, s1, a.sx);
+    a.sx2 = fma((double)sy2[0] + 2.0 * (double)sry[0] + (double)sr8q, s2, a.sx2);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        a.sy[f] = fma((double)sy[f], s1, a.sy[f]);
+        a.sy2[f] = fma((double)sy2[f], s2, a.sy2[f]);
+        a.sxy[f] = fma((double)sy2[f] + (double)sry[f], s2, a.sxy[f]);
+        a.sab[f] = fma((double)sab[f], s1, a.sab[f]);
+        a.amax[f] = fmaxf(a.amax[f], mx[f] * s1f);
+    }
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) {
+    return __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v), m),
+                            __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v), m));
+}
+
+template <bool VEC>
+__device__ __forceinline__ void load_row_group(const uint16_t* __restrict__ x, int64_t row, int64_t col0,
+                                               int64_t cols, int64_t ld, uint32_t (&w)[8]) {
+    if (VEC) {
+        ldg256(x + row * ld + col0, w);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t c = col0 + 2 * i;
+            const uint32_t lo = c < cols ? x[row * ld + c] : 0u;
+            const uint32_t hi = c + 1 < cols ? x[row * ld + c + 1] : 0u;
+            w[i] = lo | (hi << 16);
+        }
+    }
+}
+
+constexpr int FAST_WARPS = 4;
+constexpr int FAST_UNROLL = 4;
+
+template <bool VEC>
+__global__ void __launch_bounds__(FAST_WARPS * 32) stats_fast_kernel(
+    const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
+    int64_t chunks, int64_t nitems, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * FAST_WARPS + (threadIdx.x >> 5);
+    if (item >= nitems) return;
+    const int64_t tr = item / chunks;
+    const int64_t ck = item - tr * chunks;
+    const int64_t col0 = ck * 512 + (int64_t)lane * GROUP;
+    const int64_t row0 = tr * TILE;
+    const int nrows = (int)min((int64_t)TILE, rows - row0);
+    TileAcc a;
+    acc_zero(a);
+    if (col0 < cols) {
+        uint32_t cur[FAST_UNROLL][8];
+        int r = 0;
+        for (; r + FAST_UNROLL <= nrows; r += FAST_UNROLL) {
+#pragma unroll
+            for (int k = 0; k < FAST_UNROLL; ++k) load_row_group<VEC>(x, row0 + r + k, col0, cols, ld, cur[k]);
+#pragma unroll
+            for (int k = 0; k < FAST_UNROLL; ++k) group_fast(cur[k], a);
+        }
+        for (; r < nrows; ++r) {
+            load_row_group<VEC>(x, row0 + r, col0, cols, ld, cur[0]);
+            group_fast(cur[0], a);
+        }
+    }
+    // lanes 2j and 2j+1 hold the two halves of tile j
+    a.sx += shfl_xor_d(a.sx, 1);
+    a.sx2 += shfl_xor_d(a.sx2, 1);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        a.sy[f] += shfl_xor_d(a.sy[f], 1);
+        a.sy2[f] += shfl_xor_d(a.sy2[f], 1);
+        a.sxy[f] += shfl_xor_d(a.sxy[f], 1);
+        a.sab[f] += shfl_xor_d(a.sab[f], 1);
+        a.amax[f] = fmaxf(a.amax[f], __shfl_xor_sync(0xFFFFFFFFu, a.amax[f], 1));
+    }
+    const int64_t tc = ck * 16 + (lane >> 1);
+    if ((lane & 1) == 0 && tc < tiles_w) {
+        const int64_t t = tr * tiles_w + tc;
+        table[QA_STAT_SX * ntiles + t] = a.sx;
+        table[QA_STAT_SX2 * ntiles + t] = a.sx2;
+        if (fmt_mask & 1u) {  // bf16-exact input: y == x
+            table[QA_STAT_FMT(0, 0) * ntiles + t] = a.sx;
+            table[QA_STAT_FMT(0, 1) * ntiles + t] = a.sx2;
+            table[QA_STAT_FMT(0, 2) * ntiles + t] = a.sx2;
+            table[QA_STAT_FMT(0, 3) * ntiles + t] = 0.0;
+            table[QA_STAT_FMT(0, 4) * ntiles + t] = 0.0;
+        }
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            if (fmt_mask & (2u << f)) {
+                table[QA_STAT_FMT(f + 1, 0) * ntiles + t] = a.sy[f];
+                table[QA_STAT_FMT(f + 1, 1) * ntiles + t] = a.sy2[f];
+                table[QA_STAT_FMT(f + 1, 2) * ntiles + t] = a.sxy[f];
+                table[QA_STAT_FMT(f + 1, 3) * ntiles + t] = a.sab[f];
+                table[QA_STAT_FMT(f + 1, 4) * ntiles + t] = (double)a.amax[f];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// STRICT
+// ------------------------------------------------------------------------------------------
+constexpr int SP = 33;  // padded smem row pitch
+
+struct View {
+    int r0, nr, nc;  // rows [r0, r0+nr), cols [0, nc)
+};
+
+// value of statistic `kind` at flattened index i of a view (float32 arithmetic as NumPy does it)
+__device__ __forceinline__ double strict_term(const float* xs, const float* ys, const View& v, int i, int kind) {
+    const int r = v.r0 + i / v.nc, c = i % v.nc;
+    const float x = xs[r * SP + c];
+    if (kind == 0) return (double)x;
+    if (kind == 1) return (double)__fmul_rn(x, x);
+    const float y = ys[r * SP + c];
+    if (kind == 2) return (double)y;
+    if (kind == 3) return (double)__fmul_rn(y, y);
+    if (kind == 4) return (double)__fmul_rn(x, y);
+    return (double)fabsf(__fsub_rn(x, y));
+}
+
+// NumPy pairwise leaf (n <= 128) starting at flattened index lo
+__device__ double strict_leaf(const float* xs, const float* ys, const View& v, int lo, int n, int kind) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, strict_term(xs, ys, v, lo + i, kind));
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = strict_term(xs, ys, v, lo + k, kind);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], strict_term(xs, ys, v, lo + i + k, kind));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, strict_term(xs, ys, v, lo + i, kind));
+    return res;
+}
+
+// enumerate the leaves of NumPy's recursion over n elements (at most 16 for n <= 1024)
+__device__ int strict_leaves(int n, int* lo, int* len) {
+    int cnt = 0, sp = 0;
+    int st_lo[16], st_n[16];
+    st_lo[0] = 0; st_n[0] = n; sp = 1;
+    while (sp) {
+        --sp;
+        const int l = st_lo[sp], m = st_n[sp];
+        if (m <= 128) { lo[cnt] = l; len[cnt] = m; ++cnt; continue; }
+        int n2 = m / 2; n2 -= n2 % 8;
+        st_lo[sp] = l + n2; st_n[sp] = m - n2; ++sp;   // right pushed first, so left pops first
+        st_lo[sp] = l; st_n[sp] = n2; ++sp;
+    }
+    return cnt;
+}
+
+// combine leaf sums with the recursion's tree: sum(n) = sum(left n2) + sum(right)
+__device__ double strict_combine(const double* leaf, int& li, int n) {
+    if (n <= 128) return leaf[li++];
+    int n2 = n / 2; n2 -= n2 % 8;
+    const double a = strict_combine(leaf, li, n2);
+    const double b = strict_combine(leaf, li, n - n2);
+    return __dadd_rn(a, b);
+}
+
+constexpr int STRICT_WARPS = 4;
+
+template <int DT>
+__global__ void __launch_bounds__(STRICT_WARPS * 32) stats_strict_kernel(
+    const void* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w, int64_t ntiles,
+    int64_t vec_tail, uint32_t fmt_mask, double* __restrict__ table) {
+    __shared__ float xs_all[STRICT_WARPS][TILE * SP];
+    __shared__ float ys_all[STRICT_WARPS][TILE * SP];
+    __shared__ double leaf_all[STRICT_WARPS][6][16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * STRICT_WARPS + warp;
+    if (t >= ntiles) return;
+    float* xs = xs_all[warp];
+    float* ys = ys_all[warp];
+    const int64_t tr = t / tiles_w, tc = t - tr * tiles_w;
+    const int64_t row0 = tr * TILE, colb = tc * TILE;
+    const int r_end = (int)min((int64_t)TILE, rows - row0);
+    const int c_end = (int)min((int64_t)TILE, cols - colb);
+    // stage the zero-padded tile
+    for (int r = 0; r < TILE; ++r) {
+        float v = 0.f;
+        if (r < r_end && lane < c_end) {
+            if (DT == QA_DT_BF16)
+                v = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(x)[(row0 + r) * ld + colb + lane] << 16);
+            else
+                v = reinterpret_cast<const float*>(x)[(row0 + r) * ld + colb + lane];
+        }
+        xs[r * SP + lane] = v;
+    }
+    __syncwarp();
+    // the views the reference sums over (mixed_tile_greedy.py:122-131)
+    View views[2];
+    int nviews = 1;
+    const bool last_tr = (row0 + r_end == rows);
+    if (vec_tail > 0 && vec_tail < TILE && last_tr) {
+        nviews = 0;
+        if (r_end - 1 > 0) views[nviews++] = View{0, r_end - 1, c_end};
+        views[nviews++] = View{r_end - 1, 1, (int)vec_tail};
+    } else {
+        views[0] = View{0, r_end, c_end};
+    }
+
+    auto reduce_kinds = [&](int kind_lo, int nkinds, double* out) {
+        // out[k] = 0.0 + sum(view0) (+ sum(view1)), each sum in NumPy pairwise order
+        for (int k = 0; k < nkinds; ++k) out[k] = 0.0;
+        for (int vi = 0; vi < nviews; ++vi) {
+            const View v = views[vi];
+            const int n = v.nr * v.nc;
+            int lo[16], len[16];
+            const int nl = strict_leaves(n, lo, len);
+            // (kind, leaf) pairs spread over lanes
+            for (int job = lane; job < nkinds * nl; job += 32) {
+                const int k = job / nl, li = job - k * nl;
+                leaf_all[warp][k][li] = strict_leaf(xs, ys, v, lo[li], len[li], kind_lo + k);
+            }
+            __syncwarp();
+            for (int k = 0; k < nkinds; ++k) {
+                int li = 0;
+                const double s = n > 0 ? strict_combine(leaf_all[warp][k], li, n) : 0.0;
+                out[k] = __dadd_rn(out[k], s);
+            }
+            __syncwarp();
+        }
+    };
+
+    double res[4];
+    reduce_kinds(0, 2, res);
+    if (lane == 0) {
+        table[QA_STAT_SX * ntiles + t] = res[0];
+        table[QA_STAT_SX2 * ntiles + t] = res[1];
+    }
+    for (int f = 0; f < QA_NFMT; ++f) {
+        if (!((fmt_mask >> f) & 1u)) continue;
+        // quantize the tile: 64 groups, two per lane
+        __syncwarp();
+        for (int g = lane; g < 64; g += 32) {
+            const int r = g >> 1, c0 = (g & 1) * GROUP;
+            uint32_t u[GROUP];
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) u[i] = __float_as_uint(xs[r * SP + c0 + i]);
+            const uint32_t E = group_max_exp(u);
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) ys[r * SP + c0 + i] = __uint_as_float(recon_bits(f, u[i], E));
+        }
+        __syncwarp();
+        reduce_kinds(2, 4, res);
+        // max |x - y| over the views (float32, order-free)
+        float mx = 0.f;
+        for (int vi = 0; vi < nviews; ++vi) {
+            const View v = views[vi];
+            for (int i = lane; i < v.nr * v.nc; i += 32) {
+                const int r = v.r0 + i / v.nc, c = i % v.nc;
+                mx = fmaxf(mx, fabsf(__fsub_rn(xs[r * SP + c], ys[r * SP + c])));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        if (lane == 0) {
+            table[QA_STAT_FMT(f, 0) * ntiles + t] = res[0];
+            table[QA_STAT_FMT(f, 1) * ntiles + t] = res[1];
+            table[QA_STAT_FMT(f, 2) * ntiles + t] = res[2];
+            table[QA_STAT_FMT(f, 3) * ntiles + t] = res[3];
+            table[QA_STAT_FMT(f, 4) * ntiles + t] = (double)mx;
+        }
+    }
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+extern "C" int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                             int64_t vec_tail, uint32_t fmt_mask, int mode, double* table,
+                             qa_stream_t stream) {
+    if (rows < 0 || cols < 0 || ld < cols || !table) { set_error("qa_tile_stats: bad args"); return 1; }
+    if (rows == 0 || cols == 0) return 0;
+    fmt_mask &= 0xFu;
+    const int64_t tiles_h = cdiv(rows, TILE), tiles_w = cdiv(cols, TILE), ntiles = tiles_h * tiles_w;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == QA_STATS_FAST) {
+        if (x_dtype != QA_DT_BF16) { set_error("qa_tile_stats: fast mode needs bf16 input (use QA_STATS_STRICT for fp32)"); return 1; }
+        const int64_t chunks = cdiv(cols, 512), nitems = tiles_h * chunks;
+        const int64_t grid = cdiv(nitems, FAST_WARPS);
+        const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
+        const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
+        if (vec) stats_fast_kernel<true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        else stats_fast_kernel<false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        return check_launch("qa_tile_stats(fast)");
+    }
+    if (mode != QA_STATS_STRICT) { set_error("qa_tile_stats: bad mode"); return 1; }
+    const int64_t grid = cdiv(ntiles, STRICT_WARPS);
+    if (x_dtype == QA_DT_BF16)
+        stats_strict_kernel<QA_DT_BF16><<<(unsigned)grid, STRICT_WARPS * 32, 0, s>>>(x, rows, cols, ld, tiles_w, ntiles, vec_tail, fmt_mask, table);
+    else if (x_dtype == QA_DT_F32)
+        stats_strict_kernel<QA_DT_F32><<<(unsigned)grid, STRICT_WARPS * 32, 0, s>>>(x, rows, cols, ld, tiles_w, ntiles, vec_tail, fmt_mask, table);
+    else { set_error("qa_tile_stats: bad dtype"); return 1; }
+    return check_launch("qa_tile_stats(strict)");
+}

@@ -1,0 +1,274 @@
+"""Device engine: marshals tensors to the C ABI (include/qa_b200.h).  PyTorch is plumbing only
+(device memory, streams); all arithmetic on the path happens in libqa_b200.so kernels.
+
+Geometry.  The quantizers treat an n-d tensor as rows of its last axis (groups of 16 never
+cross a row; quantization_formats.py:89-119).  The mixed-tile algorithms tile
+``[prod(shape[:-1]), W]`` (1-D: rows of 32, zero-padded; tile_utils.py:91-115).  ``Prepared``
+holds a device copy in the tile geometry; for >= 2-D inputs the two geometries coincide.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import METRIC_CODE, NFMT, NSTAT, QA_DT_BF16, QA_DT_F32, STATS_FAST, STATS_STRICT, check
+
+MIXED_FORMATS = ("bf16", "bfp8", "bfp4", "bfp2")
+FMT_INDEX = {f: i for i, f in enumerate(MIXED_FORMATS)}
+TILE = 32
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.QaError("CUDA device required: the quantize-and-score path has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def fmt_mask(formats) -> int:
+    m = 0
+    for f in formats:
+        m |= 1 << FMT_INDEX[f]
+    return m
+
+
+@dataclass
+class Prepared:
+    """A tensor resident on the device in [rows, cols] row-major layout."""
+    data: torch.Tensor          # bfloat16 or float32, contiguous, rows*cols elements
+    dtype_code: int             # QA_DT_BF16 / QA_DT_F32
+    rows: int
+    cols: int
+    numel: int                  # elements of the original tensor
+    shape: tuple                # original shape
+    kind: str                   # "nd" | "vector" | "scalar"
+    vec_tail: int = 0           # valid elements in the ragged last row of a 1-D input (0: none)
+
+    @property
+    def tiles_h(self) -> int:
+        return -(-self.rows // TILE)
+
+    @property
+    def tiles_w(self) -> int:
+        return -(-self.cols // TILE)
+
+    @property
+    def ntiles(self) -> int:
+        return self.tiles_h * self.tiles_w
+
+
+def to_device(x, want_bf16: bool = True) -> tuple[torch.Tensor, int]:
+    """Host fp32 ndarray / torch tensor -> contiguous device tensor (bf16 when exactly representable)."""
+    dev = _require_cuda()
+    if isinstance(x, torch.Tensor):
+        t = x.detach()
+        if t.dtype == torch.bfloat16:
+            return t.to(dev).contiguous(), QA_DT_BF16
+        t = t.to(device=dev, dtype=torch.float32).contiguous()
+    else:
+        a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        t = torch.from_numpy(a).to(dev, non_blocking=False)
+    if not want_bf16 or t.numel() == 0:
+        return t, QA_DT_F32
+    out = torch.empty(t.shape, dtype=torch.bfloat16, device=dev)
+    bad = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(_lib.lib().qa_f32_to_bf16_checked(_ptr(t), t.numel(), _ptr(out), _ptr(bad), _stream()), "qa_f32_to_bf16_checked")
+    if int(bad.item()) == 0:
+        return out, QA_DT_BF16
+    return t, QA_DT_F32
+
+
+def prepare_rows(x) -> Prepared:
+    """Quantizer geometry: rows of the last axis (1-D: one row)."""
+    shape = tuple(x.shape)
+    t, code = to_device(x)
+    if len(shape) == 0:
+        rows, cols, kind = 1, 1, "scalar"
+    elif len(shape) == 1:
+        rows, cols, kind = 1, shape[0], "vector"
+    else:
+        rows, cols, kind = int(np.prod(shape[:-1])), shape[-1], "nd"
+    return Prepared(t.reshape(-1), code, rows, cols, int(np.prod(shape)) if shape else 1, shape, kind)
+
+
+def prepare_tiles(x) -> Prepared:
+    """Mixed-tile geometry (tile_utils.py:91-115)."""
+    shape = tuple(x.shape)
+    t, code = to_device(x)
+    numel = int(np.prod(shape)) if shape else 1
+    if len(shape) == 0:
+        return Prepared(t.reshape(-1), code, 1, 1, 1, shape, "scalar")
+    if len(shape) == 1:
+        n = shape[0]
+        rows = -(-n // TILE)
+        if rows * TILE != n:
+            pad = torch.zeros(rows * TILE, dtype=t.dtype, device=t.device)
+            pad[:n] = t
+            t = pad
+        tail = n % TILE
+        return Prepared(t.reshape(-1), code, rows, TILE, numel, shape, "vector", vec_tail=tail)
+    return Prepared(t.reshape(-1), code, int(np.prod(shape[:-1])), shape[-1], numel, shape, "nd")
+
+
+# --------------------------------------------------------------------------------------------
+# kernels
+# --------------------------------------------------------------------------------------------
+def quant_recon(p: Prepared, formats) -> dict[str, torch.Tensor]:
+    """bf16 reconstructions for `formats` (subset of MIXED_FORMATS) in one pass."""
+    formats = [f for f in formats if f in FMT_INDEX]
+    outs: dict[str, torch.Tensor] = {}
+    arr = (C.c_void_p * NFMT)()
+    for f in formats:
+        o = torch.empty(p.rows * p.cols, dtype=torch.bfloat16, device=p.data.device)
+        outs[f] = o
+        arr[FMT_INDEX[f]] = o.data_ptr()
+    if p.rows * p.cols and formats:
+        check(_lib.lib().qa_quant_recon(_ptr(p.data), p.dtype_code, p.rows, p.cols, p.cols, fmt_mask(formats), arr, _stream()),
+              "qa_quant_recon")
+    return outs
+
+
+def tile_stats(p: Prepared, formats=MIXED_FORMATS, strict: bool | None = None) -> torch.Tensor:
+    """float64 [NSTAT, ntiles] tile-stat table.  strict=None picks fast for bf16 input."""
+    if strict is None:
+        strict = p.dtype_code != QA_DT_BF16
+    table = torch.zeros((NSTAT, p.ntiles), dtype=torch.float64, device=p.data.device)
+    mode = STATS_STRICT if strict else STATS_FAST
+    check(_lib.lib().qa_tile_stats(_ptr(p.data), p.dtype_code, p.rows, p.cols, p.cols, p.vec_tail, fmt_mask(formats), mode,
+                                   _ptr(table), _stream()), "qa_tile_stats")
+    return table
+
+
+def tile_scores(p: Prepared, formats=MIXED_FORMATS) -> torch.Tensor:
+    """float32 [3 metrics, NFMT, ntiles] NumPy-faithful padded-tile scores."""
+    s = torch.zeros((3, NFMT, p.ntiles), dtype=torch.float32, device=p.data.device)
+    check(_lib.lib().qa_tile_scores_f32(_ptr(p.data), p.dtype_code, p.rows, p.cols, p.cols, fmt_mask(formats), _ptr(s), _stream()),
+          "qa_tile_scores_f32")
+    return s
+
+
+def make_rng(seed: int, device=None) -> torch.Tensor:
+    """Device-resident qa_pcg64 seeded like np.random.default_rng(seed) (SeedSequence on host)."""
+    device = device or _require_cuda()
+    st = np.random.default_rng(seed).bit_generator.state
+    s, inc = int(st["state"]["state"]), int(st["state"]["inc"])
+    m64 = (1 << 64) - 1
+    words = np.array([s >> 64, s & m64, inc >> 64, inc & m64,
+                      (int(st["has_uint32"]) & 0xFFFFFFFF) | ((int(st["uinteger"]) & 0xFFFFFFFF) << 32)], dtype=np.uint64)
+    return torch.from_numpy(words.view(np.int64).copy()).to(device)
+
+
+def numpy_permutation(rng: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.int32, device=rng.device)
+    work = torch.empty(2 * max(n, 1), dtype=torch.int32, device=rng.device)
+    check(_lib.lib().qa_numpy_permutation(_ptr(rng), n, _ptr(out), _ptr(work), _stream()), "qa_numpy_permutation")
+    return out
+
+
+def numpy_integers(rng: torch.Tensor, k: int, n: int) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.int8, device=rng.device)
+    check(_lib.lib().qa_numpy_integers(_ptr(rng), k, n, _ptr(out), _stream()), "qa_numpy_integers")
+    return out
+
+
+def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor):
+    """-> (assignment int8[ntiles], counts int64[4], state float64[8]) on device."""
+    nt = table.shape[1]
+    dev = table.device
+    assignment = torch.empty(nt, dtype=torch.int8, device=dev)
+    counts = torch.zeros(NFMT, dtype=torch.int64, device=dev)
+    state = torch.zeros(8, dtype=torch.float64, device=dev)
+    work = torch.empty(_lib.lib().qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
+    order = _lib.int32_array([FMT_INDEX[f] for f in fmt_order])
+    check(_lib.lib().qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),
+                                      _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work), _stream()),
+          "qa_greedy_assign")
+    return assignment, counts, state
+
+
+def threshold_assign(scores_metric: torch.Tensor, order_fmts, is_pcc: bool, thresholds) -> tuple[torch.Tensor, torch.Tensor]:
+    """scores_metric float32 [NFMT, ntiles]; thresholds: iterable of floats (cast to float32 like NumPy 2).
+    -> (assignment int8 [nthr, ntiles], counts int64 [nthr, 4])."""
+    nt = scores_metric.shape[1]
+    dev = scores_metric.device
+    thr = torch.tensor(np.asarray(list(thresholds), dtype=np.float32), device=dev)
+    nthr = thr.numel()
+    assignment = torch.empty((nthr, nt), dtype=torch.int8, device=dev)
+    counts = torch.zeros((nthr, NFMT), dtype=torch.int64, device=dev)
+    order = _lib.int32_array([FMT_INDEX[f] for f in order_fmts])
+    check(_lib.lib().qa_threshold_assign(_ptr(scores_metric), nt, order, len(order_fmts), 1 if is_pcc else 0, _ptr(thr), nthr,
+                                         _ptr(assignment), _ptr(counts), _stream()), "qa_threshold_assign")
+    return assignment, counts
+
+
+def random_samples(table: torch.Tensor, numel: int, fmt_list, iters: int, rng: torch.Tensor):
+    """-> (choices int8 [iters, ntiles], metrics f64 [iters, 3], counts int64 [iters, 4])."""
+    nt = table.shape[1]
+    dev = table.device
+    k = len(fmt_list)
+    choices = torch.empty((iters, nt), dtype=torch.int8, device=dev)
+    ready = 0
+    if k & (k - 1):  # rejection sampling possible: draw sequentially on device, then map to format indices
+        raw = numpy_integers(rng, k, iters * nt)
+        lut = torch.tensor([FMT_INDEX[f] for f in fmt_list], dtype=torch.int8, device=dev)
+        choices = lut[raw.long()].reshape(iters, nt).contiguous()
+        ready = 1
+    metrics = torch.zeros((iters, 3), dtype=torch.float64, device=dev)
+    counts = torch.zeros((iters, NFMT), dtype=torch.int64, device=dev)
+    idx = _lib.int32_array([FMT_INDEX[f] for f in fmt_list])
+    check(_lib.lib().qa_random_samples(_ptr(table), nt, float(numel), idx, k, iters, _ptr(rng), _ptr(choices), ready,
+                                       _ptr(metrics), _ptr(counts), _stream()), "qa_random_samples")
+    return choices, metrics, counts
+
+
+def apply_assignment(p: Prepared, assignment: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(p.rows * p.cols, dtype=torch.bfloat16, device=p.data.device)
+    a = assignment.to(torch.int8).contiguous().reshape(-1)
+    check(_lib.lib().qa_apply_assignment(_ptr(p.data), p.dtype_code, p.rows, p.cols, p.cols, _ptr(a), _ptr(out), _stream()),
+          "qa_apply_assignment")
+    return out
+
+
+def assignment_sums(table: torch.Tensor, assignment: torch.Tensor | None = None, fmt: int = -1) -> torch.Tensor:
+    out = torch.zeros(8, dtype=torch.float64, device=table.device)
+    a = None if assignment is None else assignment.to(torch.int8).contiguous().reshape(-1)
+    check(_lib.lib().qa_assignment_sums(_ptr(table), table.shape[1], _ptr(a), int(fmt), _ptr(out), _stream()),
+          "qa_assignment_sums")
+    return out
+
+
+def metrics_from_sums(s, numel: int) -> dict:
+    """pcc / mae / atol from {sx, sx2, sy, sy2, sxy, sabs, max}: float64 recombination of the
+    formulas in metrics.py:6-27 (the mathematically exact value the reference's float32 approximates)."""
+    sx, sx2, sy, sy2, sxy, sabs, amax = [float(v) for v in s[:7]]
+    n = float(numel)
+    if n == 0:
+        return {"pcc": 1.0, "mae": 0.0, "atol": 0.0}
+    am2 = max(sx2 - sx * sx / n, 0.0)
+    bm2 = max(sy2 - sy * sy / n, 0.0)
+    den = math.sqrt(am2 * bm2)
+    if den == 0.0:
+        pcc = 1.0 if amax == 0.0 else 0.0
+    else:
+        pcc = (sxy - sx * sy / n) / den
+    return {"pcc": pcc, "mae": sabs / n, "atol": amax}
+
+
+def result_to_numpy(p: Prepared, y_bf16: torch.Tensor) -> np.ndarray:
+    """Device bf16 reconstruction in p's geometry -> float32 ndarray of the original shape."""
+    y = y_bf16.reshape(-1)
+    if p.kind == "vector" and y.numel() != p.numel:
+        y = y[: p.numel]
+    return y.to(torch.float32).cpu().numpy().reshape(p.shape)
