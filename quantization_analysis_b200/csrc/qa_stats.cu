@@ -12,8 +12,9 @@
 // partials are widened to float64 and scaled by 2^(E-134) or its square, so the per-tile float64
 // sums are exact whenever they are representable - which is also when NumPy's pairwise float64
 // sums in the reference are exact, making the two bit-identical in that (normal) case.
-//   sum x   = (sum y8 + sum r8) * s         sum x^2 = (sum y8^2 + 2 sum r8 y8 + sum r8^2) * s^2
-//   sum x y = (sum y^2 + sum r y) * s^2
+//   sum x y = (sum y^2 + sum r y) * s^2      sum |x-y| = sum |x| - (sum (|X| - |r|)) * s
+// sum x, sum x^2 and sum |x| involve elements arbitrarily far below the group maximum, so they
+// are accumulated per element in float64 (B200 runs DFMA at 64/clk/SM on its own pipe).
 //
 // STRICT kernel (bf16 or fp32 input).  One warp per tile; float32 products and float64 sums in
 // NumPy's pairwise order over the flattened valid view(s) of the tile, i.e. the same roundings
@@ -65,6 +66,7 @@ template <> struct Fmt<0> { static constexpr float M = 25165824.f, L = 254.f; };
 template <> struct Fmt<1> { static constexpr float M = 402653184.f, L = 224.f; };    // bfp4: step 32
 template <> struct Fmt<2> { static constexpr float M = 1610612736.f, L = 128.f; };   // bfp2: step 128
 
+template <bool EXACT_ABS>
 __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     // shared exponent: max of |bf16| patterns, two per word
     uint32_t m = 0;
@@ -80,48 +82,48 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     const float inv = __uint_as_float((261u - E) << 23);  // 2^(134-E)
     float sy[3] = {0.f, 0.f, 0.f}, sy2[3] = {0.f, 0.f, 0.f}, sry[3] = {0.f, 0.f, 0.f}, sab[3] = {0.f, 0.f, 0.f},
           mx[3] = {0.f, 0.f, 0.f};
-    float sr8 = 0.f, sr8q = 0.f;
+    double gx = 0.0, gx2 = 0.0, gax = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float x = __uint_as_float(h ? (w[i] & 0xFFFF0000u) : (w[i] << 16));
+            // sum x, sum x^2 (and sum |x|): float64 per element - exact whatever the exponent spread
+            const double xd = (double)x;
+            gx += xd;
+            gx2 = fma(xd, xd, gx2);
+            if (EXACT_ABS) gax += fabs(xd);
             const float X = x * inv;
-            {
-                float y = (X + Fmt<0>::M) - Fmt<0>::M;
-                y = fminf(fmaxf(y, -Fmt<0>::L), Fmt<0>::L);
-                const float r = X - y;
-                sy[0] += y; sy2[0] = fmaf(y, y, sy2[0]); sry[0] = fmaf(r, y, sry[0]);
-                sab[0] += fabsf(r); mx[0] = fmaxf(mx[0], fabsf(r));
-                sr8 += r; sr8q = fmaf(r, r, sr8q);
+            const float aX = fabsf(X);
+#define QA_FMT_STEP(F)                                                                      \
+            {                                                                               \
+                float y = (X + Fmt<F>::M) - Fmt<F>::M;                                      \
+                y = fminf(fmaxf(y, -Fmt<F>::L), Fmt<F>::L);                                 \
+                const float r = X - y;                                                      \
+                sy[F] += y; sy2[F] = fmaf(y, y, sy2[F]); sry[F] = fmaf(r, y, sry[F]);       \
+                /* EXACT_ABS: accumulate |X| - |r| (0 for elements every format flushes,   \
+                   a short dyadic otherwise) and subtract it from the float64 sum |x| */    \
+                sab[F] += EXACT_ABS ? (aX - fabsf(r)) : fabsf(r);                           \
+                mx[F] = fmaxf(mx[F], fabsf(r));                                             \
             }
-            {
-                float y = (X + Fmt<1>::M) - Fmt<1>::M;
-                y = fminf(fmaxf(y, -Fmt<1>::L), Fmt<1>::L);
-                const float r = X - y;
-                sy[1] += y; sy2[1] = fmaf(y, y, sy2[1]); sry[1] = fmaf(r, y, sry[1]);
-                sab[1] += fabsf(r); mx[1] = fmaxf(mx[1], fabsf(r));
-            }
-            {
-                float y = (X + Fmt<2>::M) - Fmt<2>::M;
-                y = fminf(fmaxf(y, -Fmt<2>::L), Fmt<2>::L);
-                const float r = X - y;
-                sy[2] += y; sy2[2] = fmaf(y, y, sy2[2]); sry[2] = fmaf(r, y, sry[2]);
-                sab[2] += fabsf(r); mx[2] = fmaxf(mx[2], fabsf(r));
-            }
+            QA_FMT_STEP(0)
+            QA_FMT_STEP(1)
+            QA_FMT_STEP(2)
+#undef QA_FMT_STEP
         }
     }
     const double s1 = __hiloint2double((int)((E + 889u) << 20), 0);        // 2^(E-134)
     const double s2 = __hiloint2double((int)((2u * E + 755u) << 20), 0);   // 2^(2E-268)
     const float s1f = __uint_as_float((E - 7u) << 23);
-    a.sx = fma((double)sy[0] + (double)sr8, s1, a.sx);
-    a.sx2 = fma((double)sy2[0] + 2.0 * (double)sry[0] + (double)sr8q, s2, a.sx2);
+    a.sx += gx;
+    a.sx2 += gx2;
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
         a.sy[f] = fma((double)sy[f], s1, a.sy[f]);
         a.sy2[f] = fma((double)sy2[f], s2, a.sy2[f]);
         a.sxy[f] = fma((double)sy2[f] + (double)sry[f], s2, a.sxy[f]);
-        a.sab[f] = fma((double)sab[f], s1, a.sab[f]);
+        if (EXACT_ABS) a.sab[f] += fma(-(double)sab[f], s1, gax);
+        else a.sab[f] = fma((double)sab[f], s1, a.sab[f]);
         a.amax[f] = fmaxf(a.amax[f], mx[f] * s1f);
     }
 }
@@ -150,7 +152,7 @@ __device__ __forceinline__ void load_row_group(const uint16_t* __restrict__ x, i
 constexpr int FAST_WARPS = 4;
 constexpr int FAST_UNROLL = 4;
 
-template <bool VEC>
+template <bool VEC, bool EXACT_ABS>
 __global__ void __launch_bounds__(FAST_WARPS * 32) stats_fast_kernel(
     const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
     int64_t chunks, int64_t nitems, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
@@ -171,11 +173,11 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) stats_fast_kernel(
 #pragma unroll
             for (int k = 0; k < FAST_UNROLL; ++k) load_row_group<VEC>(x, row0 + r + k, col0, cols, ld, cur[k]);
 #pragma unroll
-            for (int k = 0; k < FAST_UNROLL; ++k) group_fast(cur[k], a);
+            for (int k = 0; k < FAST_UNROLL; ++k) group_fast<EXACT_ABS>(cur[k], a);
         }
         for (; r < nrows; ++r) {
             load_row_group<VEC>(x, row0 + r, col0, cols, ld, cur[0]);
-            group_fast(cur[0], a);
+            group_fast<EXACT_ABS>(cur[0], a);
         }
     }
     // lanes 2j and 2j+1 hold the two halves of tile j
@@ -407,8 +409,8 @@ extern "C" int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t c
         const int64_t grid = cdiv(nitems, FAST_WARPS);
         const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
         const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
-        if (vec) stats_fast_kernel<true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
-        else stats_fast_kernel<false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        if (vec) stats_fast_kernel<true, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        else stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
         return check_launch("qa_tile_stats(fast)");
     }
     if (mode != QA_STATS_STRICT) { set_error("qa_tile_stats: bad mode"); return 1; }

@@ -76,22 +76,23 @@ def test_tile_stats_strict_bit_exact(qa, name):
 
 @pytest.mark.parametrize("name", G.algo_case_names())
 def test_tile_stats_fast_matches_oracle(qa, name):
+    """Fast table vs the NumPy-order oracle: every sum whose float64 value is exactly representable
+    must be bit-identical; sum x^2 over tiles with a very wide exponent spread is order-dependent
+    in float64 even in NumPy, so it is held to 1e-13 relative (a few ulp)."""
     eng = qa["engine"]
     x = G.algo_input(name)
     want = orc.tile_stat_table(x)
     p = eng.prepare_tiles(x)
     assert p.dtype_code == 0
     got = _table_from_device(eng.tile_stats(p, G.MIXED, strict=False), None)
-    pairs = [(got["sx"], want["sx"]), (got["sx2"], want["sx2"])]
+    assert np.array_equal(got["sx"], want["sx"]), name
+    assert np.allclose(got["sx2"], want["sx2"], rtol=1e-13, atol=0), name
     for f in G.MIXED:
-        pairs += [(got[f][k], want[f][k]) for k in ("sy", "sy2", "sxy", "sabs", "amax")]
-    exact = total = 0
-    for g, w in pairs:
-        scale = np.maximum(np.abs(w), 1e-300)
-        # sums with cancellation (sx, sy) are compared against the magnitude of sum|x|-like scale
-        assert np.all(np.abs(g - w) <= 1e-12 * np.maximum(scale, np.abs(want["bfp2"]["sabs"]) + np.abs(want["sx"]))), name
-        exact += int(np.sum(g == w)); total += g.size
-    assert exact >= 0.98 * total, (name, exact, total)
+        for k in ("sy", "sy2", "sxy", "sabs", "amax"):
+            if f == "bf16" and k in ("sy2", "sxy"):
+                assert np.allclose(got[f][k], want[f][k], rtol=1e-13, atol=0), (name, f, k)
+            else:
+                assert np.array_equal(got[f][k], want[f][k]), (name, f, k)
 
 
 @pytest.mark.parametrize("name", G.algo_case_names())
