@@ -1,0 +1,113 @@
+"""Multi-tensor batching of the quantize-and-score path (the per-tensor loop of wq:655-709).
+
+``GreedyBatch`` owns every device buffer for a list of same-run tensors and enqueues, per
+tensor, the fused tile-stat pass, the greedy assignment and the whole-tensor sums on a small
+pool of CUDA streams, with no host synchronisation until ``collect()``.  Tensors are independent
+(the reference processes them one after another), so a rank's shard is just a sub-list.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from ._lib import METRIC_CODE, NFMT, NSTAT, STATS_FAST, check
+
+MIXED = engine.MIXED_FORMATS
+
+
+class GreedyBatch:
+    def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
+                 tile_formats=MIXED, n_streams: int = 4, device=None):
+        self.device = device or engine._require_cuda()
+        self.metric, self.threshold, self.seed = metric, float(threshold), int(seed)
+        self.tile_formats = list(tile_formats)
+        self.shapes = [tuple(int(v) for v in s) for s in shapes]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        L = _lib.lib()
+        self.slots = []
+        rng0 = engine.make_rng(self.seed, self.device)
+        for (r, c) in self.shapes:
+            nt = (-(-r // 32)) * (-(-c // 32))
+            self.slots.append({
+                "rows": r, "cols": c, "ntiles": nt, "numel": r * c,
+                "x": torch.empty(r * c, dtype=torch.bfloat16, device=self.device),
+                "table": torch.zeros((NSTAT, nt), dtype=torch.float64, device=self.device),
+                "assignment": torch.empty(nt, dtype=torch.int8, device=self.device),
+                "counts": torch.zeros(NFMT, dtype=torch.int64, device=self.device),
+                "state": torch.zeros(8, dtype=torch.float64, device=self.device),
+                "sums": torch.zeros(8, dtype=torch.float64, device=self.device),
+                "work": torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=self.device),
+                "rng": rng0.clone(),
+            })
+        self._rng0 = rng0
+        self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
+        self.launches_per_step = 3 * len(self.slots)   # tile_stats + greedy + assignment_sums per tensor
+
+    # ---- data movement -------------------------------------------------------------------
+    def load_device(self, tensors) -> None:
+        """Copy bf16 tensors (host or device) into the resident input buffers."""
+        for slot, t in zip(self.slots, tensors):
+            slot["x"].copy_(t.reshape(-1), non_blocking=True)
+
+    def total_bytes(self) -> int:
+        return sum(2 * s["numel"] for s in self.slots)
+
+    # ---- compute -------------------------------------------------------------------------
+    def _enqueue(self, slot, stream, stats: bool = True, assign: bool = True) -> None:
+        L = _lib.lib()
+        sp = stream.cuda_stream
+        if stats:
+            check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
+                                  0xF, STATS_FAST, slot["table"].data_ptr(), sp), "qa_tile_stats")
+        if assign:
+            slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
+            check(L.qa_greedy_assign(slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
+                                     METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
+                                     slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
+                                     slot["state"].data_ptr(), slot["work"].data_ptr(), sp), "qa_greedy_assign")
+            check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
+                                       slot["sums"].data_ptr(), sp), "qa_assignment_sums")
+
+    def run(self, stats: bool = True, assign: bool = True) -> None:
+        """Enqueue one pass over every tensor; returns immediately (no host sync)."""
+        cur = torch.cuda.current_stream(self.device)
+        order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])   # longest chain first
+        for k, i in enumerate(order):
+            st = self.streams[k % len(self.streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                self._enqueue(self.slots[i], st, stats, assign)
+        for st in self.streams:
+            cur.wait_stream(st)
+
+    def run_from_host(self, host_tensors) -> list[dict]:
+        """End-to-end pass: pinned host bf16 -> device, quantize+score+assign, results back to host."""
+        cur = torch.cuda.current_stream(self.device)
+        order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])
+        for k, i in enumerate(order):
+            st = self.streams[k % len(self.streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
+                self._enqueue(self.slots[i], st)
+        for st in self.streams:
+            cur.wait_stream(st)
+        return self.collect()
+
+    def collect(self) -> list[dict]:
+        """Device -> host: assignment maps, counts and exact pcc/mae/atol per tensor (synchronises)."""
+        out = []
+        packs = []
+        for s in self.slots:
+            packs.append((s["assignment"].to("cpu", non_blocking=True), s["counts"].to("cpu", non_blocking=True),
+                          s["sums"].to("cpu", non_blocking=True)))
+        torch.cuda.current_stream(self.device).synchronize()
+        for s, (a, c, sums) in zip(self.slots, packs):
+            counts = {f: int(c[i]) for i, f in enumerate(MIXED)}
+            out.append({"assignment": a.numpy().reshape(-(-s["rows"] // 32), -(-s["cols"] // 32)), "counts": counts,
+                        "metrics": engine.metrics_from_sums(sums.numpy(), s["numel"])})
+        return out
+
+    def d2h_bytes(self) -> int:
+        return sum(s["ntiles"] + 8 * NFMT + 8 * 8 for s in self.slots)
