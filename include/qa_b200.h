@@ -43,6 +43,8 @@ extern "C" {
 
 #define QA_STATS_FAST 0   /* bf16 input only; exact group-scaled partial sums               */
 #define QA_STATS_STRICT 1 /* NumPy-order float64 pairwise sums (bit-faithful to the reference) */
+#define QA_STATS_FAST_APPROX_ABS 2 /* as FAST, but sum|x-y| from fp32 group partials (~1e-9 rel.):
+                                      enough for pcc/atol-driven assignment and reported mae */
 
 /* State of a numpy.random.Generator(PCG64) (bit_generator.state), resident in device memory.
  * Kernels advance it in place so successive calls continue the same stream. */

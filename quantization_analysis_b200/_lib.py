@@ -17,7 +17,7 @@ CSRC = _PKG / "csrc"
 QA_DT_BF16, QA_DT_F32 = 0, 1
 METRIC_CODE = {"pcc": 0, "mae": 1, "atol": 2}
 NFMT, NSTAT = 4, 22
-STATS_FAST, STATS_STRICT = 0, 1
+STATS_FAST, STATS_STRICT, STATS_FAST_APPROX_ABS = 0, 1, 2
 
 EXPORTS = [
     "qa_version", "qa_last_error", "qa_quant_recon", "qa_tile_stats", "qa_tile_scores_f32",

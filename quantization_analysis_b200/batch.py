@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib, engine
-from ._lib import METRIC_CODE, NFMT, NSTAT, STATS_FAST, check
+from ._lib import METRIC_CODE, NFMT, NSTAT, STATS_FAST, STATS_FAST_APPROX_ABS, check
 
 MIXED = engine.MIXED_FORMATS
 
@@ -59,7 +59,8 @@ class GreedyBatch:
         sp = stream.cuda_stream
         if stats:
             check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
-                                  0xF, STATS_FAST, slot["table"].data_ptr(), sp), "qa_tile_stats")
+                                  0xF, STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS,
+                                  slot["table"].data_ptr(), sp), "qa_tile_stats")
         if assign:
             slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
             check(L.qa_greedy_assign(slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),

@@ -45,7 +45,8 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
     def run_prepared(self, p: engine.Prepared, tile_formats, table=None, seed: int | None = None) -> mc.DeviceResult:
         """Device-resident run; `table` may be shared between algorithms on the same tensor."""
         if table is None:
-            table = engine.tile_stats(p, MIXED_TILE_FORMATS, strict=True if self.strict else None)
+            table = engine.tile_stats(p, MIXED_TILE_FORMATS, strict=True if self.strict else None,
+                                      exact_abs=(self.metric == "mae"))
         seed = self.seed if seed is None else seed
         if seed == 0:
             seed = secrets.randbits(31)           # mixed_tile_greedy.py:222-224

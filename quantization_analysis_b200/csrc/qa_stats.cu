@@ -53,7 +53,7 @@ __device__ __noinline__ void group_slow(const uint32_t (&w)[8], uint32_t E, Tile
             const float r = fabsf(__fsub_rn(x, y));
             a.sy[f] += (double)y;
             a.sy2[f] += (double)__fmul_rn(y, y);
-            a.sxy[f] += (double)__fmul_rn(x, y);
+            a.sxy[f] += (double)__fmul_rn(x, y) - (double)__fmul_rn(y, y);   // sxy holds sum (x-y)*y until the tile end
             a.sab[f] += (double)r;
             a.amax[f] = fmaxf(a.amax[f], r);
         }
@@ -66,6 +66,49 @@ template <> struct Fmt<0> { static constexpr float M = 25165824.f, L = 254.f; };
 template <> struct Fmt<1> { static constexpr float M = 402653184.f, L = 224.f; };    // bfp4: step 32
 template <> struct Fmt<2> { static constexpr float M = 1610612736.f, L = 128.f; };   // bfp2: step 128
 
+// sm_100 packed-float2 arithmetic (FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// clamp(y, -L, L) in one instruction: min(|y|, L) with the sign of y (FMNMX.XORSIGN)
+__device__ __forceinline__ float clamp_sym(float y, float L) {
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"(L));
+    return r;
+}
+__device__ __forceinline__ float max3abs(float m, float a, float b) {
+    float r;
+    asm("max.abs.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(a), "f"(b));
+    return r;
+}
+
+struct GroupAcc {   // in-group float32 partials, two lanes (even / odd element) each
+    float2 sy, sy2, sry, sab;
+    float mx;
+};
+
+template <int F, bool EXACT_ABS>
+__device__ __forceinline__ void fmt_step(const float2 X, const float2 aX, GroupAcc& g) {
+    const float2 Mv = make_float2(Fmt<F>::M, Fmt<F>::M);
+    float2 y = sub2(add2(X, Mv), Mv);                  // round to the format's step, ties to even
+    y.x = clamp_sym(y.x, Fmt<F>::L);                   // mantissa clamp (no exponent bump)
+    y.y = clamp_sym(y.y, Fmt<F>::L);
+    const float2 r = sub2(X, y);
+    g.sy = add2(g.sy, y);
+    g.sy2 = fma2(y, y, g.sy2);
+    g.sry = fma2(r, y, g.sry);
+    if (EXACT_ABS) {
+        // |X| - |r|: 0 for elements every format flushes, a short dyadic otherwise (exact in fp32)
+        g.sab.x += aX.x - fabsf(r.x);
+        g.sab.y += aX.y - fabsf(r.y);
+    } else {
+        g.sab.x += fabsf(r.x);
+        g.sab.y += fabsf(r.y);
+    }
+    g.mx = max3abs(g.mx, r.x, r.y);
+}
+
 template <bool EXACT_ABS>
 __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     // shared exponent: max of |bf16| patterns, two per word
@@ -77,40 +120,47 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     }
     const uint32_t E = max(m & 0xFFFFu, m >> 16) >> 7;
     if (E == 0u) return;                         // every element is zero/denormal: flushed (x ~ 0)
-    if (E < 24u || E == 255u) { group_slow(w, E, a); return; }
+    if (E < 24u || E == 255u) {
+        // rare: keep the caller's accumulators in registers by handing the slow path its own copy
+        TileAcc t;
+        acc_zero(t);
+        uint32_t wc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) wc[i] = w[i];
+        group_slow(wc, E, t);
+        a.sx += t.sx; a.sx2 += t.sx2;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            a.sy[f] += t.sy[f]; a.sy2[f] += t.sy2[f]; a.sxy[f] += t.sxy[f]; a.sab[f] += t.sab[f];
+            a.amax[f] = fmaxf(a.amax[f], t.amax[f]);
+        }
+        return;
+    }
 
     const float inv = __uint_as_float((261u - E) << 23);  // 2^(134-E)
-    float sy[3] = {0.f, 0.f, 0.f}, sy2[3] = {0.f, 0.f, 0.f}, sry[3] = {0.f, 0.f, 0.f}, sab[3] = {0.f, 0.f, 0.f},
-          mx[3] = {0.f, 0.f, 0.f};
+    const float2 inv2 = make_float2(inv, inv);
+    GroupAcc g[3];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+        g[f].sy = g[f].sy2 = g[f].sry = g[f].sab = make_float2(0.f, 0.f);
+        g[f].mx = 0.f;
+    }
     double gx = 0.0, gx2 = 0.0, gax = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const float x = __uint_as_float(h ? (w[i] & 0xFFFF0000u) : (w[i] << 16));
-            // sum x, sum x^2 (and sum |x|): float64 per element - exact whatever the exponent spread
-            const double xd = (double)x;
-            gx += xd;
-            gx2 = fma(xd, xd, gx2);
-            if (EXACT_ABS) gax += fabs(xd);
-            const float X = x * inv;
-            const float aX = fabsf(X);
-#define QA_FMT_STEP(F)                                                                      \
-            {                                                                               \
-                float y = (X + Fmt<F>::M) - Fmt<F>::M;                                      \
-                y = fminf(fmaxf(y, -Fmt<F>::L), Fmt<F>::L);                                 \
-                const float r = X - y;                                                      \
-                sy[F] += y; sy2[F] = fmaf(y, y, sy2[F]); sry[F] = fmaf(r, y, sry[F]);       \
-                /* EXACT_ABS: accumulate |X| - |r| (0 for elements every format flushes,   \
-                   a short dyadic otherwise) and subtract it from the float64 sum |x| */    \
-                sab[F] += EXACT_ABS ? (aX - fabsf(r)) : fabsf(r);                           \
-                mx[F] = fmaxf(mx[F], fabsf(r));                                             \
-            }
-            QA_FMT_STEP(0)
-            QA_FMT_STEP(1)
-            QA_FMT_STEP(2)
-#undef QA_FMT_STEP
-        }
+        const float2 x = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+        // sum x, sum x^2 (and sum |x|): float64 per element - exact whatever the exponent spread
+        const double x0 = (double)x.x, x1 = (double)x.y;
+        gx += x0;
+        gx += x1;
+        gx2 = fma(x0, x0, gx2);
+        gx2 = fma(x1, x1, gx2);
+        if (EXACT_ABS) { gax += fabs(x0); gax += fabs(x1); }
+        const float2 X = mul2(x, inv2);
+        const float2 aX = make_float2(fabsf(X.x), fabsf(X.y));
+        fmt_step<0, EXACT_ABS>(X, aX, g[0]);
+        fmt_step<1, EXACT_ABS>(X, aX, g[1]);
+        fmt_step<2, EXACT_ABS>(X, aX, g[2]);
     }
     const double s1 = __hiloint2double((int)((E + 889u) << 20), 0);        // 2^(E-134)
     const double s2 = __hiloint2double((int)((2u * E + 755u) << 20), 0);   // 2^(2E-268)
@@ -119,12 +169,12 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     a.sx2 += gx2;
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-        a.sy[f] = fma((double)sy[f], s1, a.sy[f]);
-        a.sy2[f] = fma((double)sy2[f], s2, a.sy2[f]);
-        a.sxy[f] = fma((double)sy2[f] + (double)sry[f], s2, a.sxy[f]);
-        if (EXACT_ABS) a.sab[f] += fma(-(double)sab[f], s1, gax);
-        else a.sab[f] = fma((double)sab[f], s1, a.sab[f]);
-        a.amax[f] = fmaxf(a.amax[f], mx[f] * s1f);
+        a.sy[f] = fma((double)(g[f].sy.x + g[f].sy.y), s1, a.sy[f]);
+        a.sy2[f] = fma((double)(g[f].sy2.x + g[f].sy2.y), s2, a.sy2[f]);
+        a.sxy[f] = fma((double)(g[f].sry.x + g[f].sry.y), s2, a.sxy[f]);   // holds sum r*y; + sum y^2 at tile end
+        if (EXACT_ABS) a.sab[f] += fma(-(double)(g[f].sab.x + g[f].sab.y), s1, gax);
+        else a.sab[f] = fma((double)(g[f].sab.x + g[f].sab.y), s1, a.sab[f]);
+        a.amax[f] = fmaxf(a.amax[f], g[f].mx * s1f);
     }
 }
 
@@ -180,6 +230,8 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) stats_fast_kernel(
             group_fast<EXACT_ABS>(cur[0], a);
         }
     }
+#pragma unroll
+    for (int f = 0; f < 3; ++f) a.sxy[f] += a.sy2[f];    // sum x*y = sum y^2 + sum (x-y)*y
     // lanes 2j and 2j+1 hold the two halves of tile j
     a.sx += shfl_xor_d(a.sx, 1);
     a.sx2 += shfl_xor_d(a.sx2, 1);
@@ -403,14 +455,17 @@ extern "C" int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t c
     fmt_mask &= 0xFu;
     const int64_t tiles_h = cdiv(rows, TILE), tiles_w = cdiv(cols, TILE), ntiles = tiles_h * tiles_w;
     cudaStream_t s = (cudaStream_t)stream;
-    if (mode == QA_STATS_FAST) {
+    if (mode == QA_STATS_FAST || mode == QA_STATS_FAST_APPROX_ABS) {
         if (x_dtype != QA_DT_BF16) { set_error("qa_tile_stats: fast mode needs bf16 input (use QA_STATS_STRICT for fp32)"); return 1; }
         const int64_t chunks = cdiv(cols, 512), nitems = tiles_h * chunks;
         const int64_t grid = cdiv(nitems, FAST_WARPS);
         const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
         const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
-        if (vec) stats_fast_kernel<true, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
-        else stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        const bool exact_abs = (mode == QA_STATS_FAST);
+        if (vec && exact_abs) stats_fast_kernel<true, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        else if (vec) stats_fast_kernel<true, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        else if (exact_abs) stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
+        else stats_fast_kernel<false, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
         return check_launch("qa_tile_stats(fast)");
     }
     if (mode != QA_STATS_STRICT) { set_error("qa_tile_stats: bad mode"); return 1; }
