@@ -104,6 +104,22 @@ int qa_greedy_assign(const double* table, int64_t ntiles, double numel, int metr
                      int8_t* assignment, int64_t* counts, double* state, void* work,
                      qa_stream_t stream);
 
+/* Same contract as qa_greedy_assign / qa_numpy_permutation, computed by ONE 1024-thread block per
+ * tensor instead of one thread: the sequentially-rounded float64 sums are carried by a prefix
+ * scan that reproduces every rounding, the accept/reject chain is resolved by speculation to its
+ * sequential fixed point, and the NumPy permutation is generated and applied in parallel
+ * (csrc/qa_greedy_par.cu).  metric: pcc or mae (atol keeps the sequential kernel).
+ * state[6] = degraded-column bits (bit0 sum x, bit1 sum y of the INITIAL sums were finished with a
+ * tree sum because they kept changing binade) + 65536 * speculation rounds.
+ * work: at least qa_greedy_par_work_bytes(n) bytes. */
+int64_t qa_greedy_par_work_bytes(int64_t n);
+int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric,
+                         double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
+                         int8_t* assignment, int64_t* counts, double* state, void* work,
+                         qa_stream_t stream);
+int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* work,
+                             qa_stream_t stream);
+
 /* Per-tile threshold assignment for nthr thresholds at once.
  * Replaces mixed_tile_threshold.py:111-123 and scripts/sweep_mixed_tile_threshold.py:145-155.
  * scores: float32[QA_NFMT][ntiles] of ONE metric; order[norder]: formats by ascending bytes;

@@ -37,7 +37,8 @@ class GreedyBatch:
                 "counts": torch.zeros(NFMT, dtype=torch.int64, device=self.device),
                 "state": torch.zeros(8, dtype=torch.float64, device=self.device),
                 "sums": torch.zeros(8, dtype=torch.float64, device=self.device),
-                "work": torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=self.device),
+                "work": torch.empty(max(L.qa_greedy_work_bytes(nt), L.qa_greedy_par_work_bytes(nt)), dtype=torch.uint8,
+                                    device=self.device),
                 "rng": rng0.clone(),
             })
         self._rng0 = rng0
@@ -63,10 +64,11 @@ class GreedyBatch:
                                   slot["table"].data_ptr(), sp), "qa_tile_stats")
         if assign:
             slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
-            check(L.qa_greedy_assign(slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
-                                     METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
-                                     slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
-                                     slot["state"].data_ptr(), slot["work"].data_ptr(), sp), "qa_greedy_assign")
+            fn = L.qa_greedy_assign if self.metric == "atol" else L.qa_greedy_assign_par
+            check(fn(slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
+                     METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
+                     slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
+                     slot["state"].data_ptr(), slot["work"].data_ptr(), sp), "qa_greedy_assign")
             check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
                                        slot["sums"].data_ptr(), sp), "qa_assignment_sums")
 

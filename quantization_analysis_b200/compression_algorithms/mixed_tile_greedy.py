@@ -25,6 +25,7 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
         self.threshold = float(self.params.get("threshold", 0.999))
         self.seed = int(self.params.get("seed", 0))
         self.strict = bool(self.params.get("strict_sums", False))   # extension: NumPy-order float64 tile sums
+        self.sequential = bool(self.params.get("sequential_chain", False))  # extension: one-thread decision chain
         self.tile_formats = mc.parse_formats(raw) if raw is not None else None
         if self.metric not in mc.VALID_METRICS:
             raise ValueError(f"Unsupported metric: {self.metric}")
@@ -51,7 +52,8 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
         if seed == 0:
             seed = secrets.randbits(31)           # mixed_tile_greedy.py:222-224
         rng = engine.make_rng(seed, p.data.device)
-        assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng)
+        assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng,
+                                                             parallel=False if self.sequential else None)
         counts = mc.counts_dict(counts_dev)
         sums = engine.assignment_sums(table, assignment)
         metrics = engine.metrics_from_sums(sums.cpu().numpy(), p.numel)

@@ -173,10 +173,16 @@ def make_rng(seed: int, device=None) -> torch.Tensor:
     return torch.from_numpy(words.view(np.int64).copy()).to(device)
 
 
-def numpy_permutation(rng: torch.Tensor, n: int) -> torch.Tensor:
+def numpy_permutation(rng: torch.Tensor, n: int, parallel: bool = True) -> torch.Tensor:
+    """np.random.Generator.permutation(n) continued from `rng` on the device (int32)."""
     out = torch.empty(n, dtype=torch.int32, device=rng.device)
-    work = torch.empty(2 * max(n, 1), dtype=torch.int32, device=rng.device)
-    check(_lib.lib().qa_numpy_permutation(_ptr(rng), n, _ptr(out), _ptr(work), _stream()), "qa_numpy_permutation")
+    L = _lib.lib()
+    if parallel:
+        work = torch.empty(L.qa_greedy_par_work_bytes(max(n, 1)), dtype=torch.uint8, device=rng.device)
+        check(L.qa_numpy_permutation_par(_ptr(rng), n, _ptr(out), _ptr(work), _stream()), "qa_numpy_permutation_par")
+    else:
+        work = torch.empty(2 * max(n, 1), dtype=torch.int32, device=rng.device)
+        check(L.qa_numpy_permutation(_ptr(rng), n, _ptr(out), _ptr(work), _stream()), "qa_numpy_permutation")
     return out
 
 
@@ -186,18 +192,29 @@ def numpy_integers(rng: torch.Tensor, k: int, n: int) -> torch.Tensor:
     return out
 
 
-def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor):
-    """-> (assignment int8[ntiles], counts int64[4], state float64[8]) on device."""
+def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor,
+                  parallel: bool | None = None):
+    """-> (assignment int8[ntiles], counts int64[4], state float64[8]) on device.
+    parallel=None: the block-parallel kernel for pcc / mae, the one-thread chain for atol."""
     nt = table.shape[1]
     dev = table.device
+    L = _lib.lib()
+    if parallel is None:
+        parallel = metric in ("pcc", "mae")
     assignment = torch.empty(nt, dtype=torch.int8, device=dev)
     counts = torch.zeros(NFMT, dtype=torch.int64, device=dev)
     state = torch.zeros(8, dtype=torch.float64, device=dev)
-    work = torch.empty(_lib.lib().qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
     order = _lib.int32_array([FMT_INDEX[f] for f in fmt_order])
-    check(_lib.lib().qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),
-                                      _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work), _stream()),
-          "qa_greedy_assign")
+    if parallel:
+        work = torch.empty(L.qa_greedy_par_work_bytes(nt), dtype=torch.uint8, device=dev)
+        check(L.qa_greedy_assign_par(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),
+                                     _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work), _stream()),
+              "qa_greedy_assign_par")
+    else:
+        work = torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
+        check(L.qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),
+                                 _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work), _stream()),
+              "qa_greedy_assign")
     return assignment, counts, state
 
 

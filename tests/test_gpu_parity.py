@@ -107,20 +107,45 @@ def test_tile_scores_bit_exact_vs_reference(qa, name):
             assert np.array_equal(s[mi, fi].view(np.uint32), want.view(np.uint32)), (name, fmt, metric)
 
 
-def test_numpy_rng_streams(qa):
+@pytest.mark.parametrize("parallel", [False, True])
+def test_numpy_rng_streams(qa, parallel):
     eng = qa["engine"]
     z = G.npz("numpy_rng.npz")
     for seed in (1, 123, 2**31 - 1):
         rng = eng.make_rng(seed)
-        assert np.array_equal(eng.numpy_permutation(rng, 10752).cpu().numpy(), z[f"s{seed}__perm_10752"])
-        assert np.array_equal(eng.numpy_permutation(rng, 777).cpu().numpy(), z[f"s{seed}__perm_777"])
+        perm = lambda n: eng.numpy_permutation(rng, n, parallel=parallel).cpu().numpy()   # noqa: E731
+        assert np.array_equal(perm(10752), z[f"s{seed}__perm_10752"])
+        assert np.array_equal(perm(777), z[f"s{seed}__perm_777"])
         assert np.array_equal(eng.numpy_integers(rng, 4, 1000).cpu().numpy(), z[f"s{seed}__int4_1000"])
         assert np.array_equal(eng.numpy_integers(rng, 3, 1000).cpu().numpy(), z[f"s{seed}__int3_1000"])
-        assert np.array_equal(eng.numpy_permutation(rng, 4096).cpu().numpy(), z[f"s{seed}__perm_4096"])
+        assert np.array_equal(perm(4096), z[f"s{seed}__perm_4096"])
         assert np.array_equal(eng.numpy_integers(rng, 2, 777).cpu().numpy(), z[f"s{seed}__int2_777"])
-        assert np.array_equal(eng.numpy_permutation(rng, 2).cpu().numpy(), z[f"s{seed}__perm_2"])
-        assert np.array_equal(eng.numpy_permutation(rng, 1).cpu().numpy(), z[f"s{seed}__perm_1"])
-        assert np.array_equal(eng.numpy_permutation(rng, 65537).cpu().numpy(), z[f"s{seed}__perm_65537"])
+        assert np.array_equal(perm(2), z[f"s{seed}__perm_2"])
+        assert np.array_equal(perm(1), z[f"s{seed}__perm_1"])
+        assert np.array_equal(perm(65537), z[f"s{seed}__perm_65537"])
+
+
+def test_parallel_greedy_equals_sequential_chain(qa):
+    """The block-parallel greedy must reproduce the one-thread chain exactly: assignment, counts,
+    final float64 state and the RNG stream position, on a tensor large enough for many chunks."""
+    from quantization_analysis_b200 import synthetic
+    eng = qa["engine"]
+    for shape, seed, maker in [((2048, 1536), 5, synthetic.randn_f32_np), ((1024, 2048), 6, synthetic.heterogeneous_f32_np)]:
+        p = eng.prepare_tiles(maker(shape, seed))
+        for metric, thr in (("pcc", 0.999), ("pcc", 0.99), ("mae", 3e-4)):
+            table = eng.tile_stats(p, G.MIXED, exact_abs=True)
+            r1, r2 = eng.make_rng(77), eng.make_rng(77)
+            a1, c1, s1 = eng.greedy_assign(table, p.numel, metric, thr, list(G.MIXED), r1, parallel=False)
+            a2, c2, s2 = eng.greedy_assign(table, p.numel, metric, thr, list(G.MIXED), r2, parallel=True)
+            assert torch.equal(a1, a2), (shape, metric, thr)
+            assert torch.equal(c1, c2)
+            assert torch.equal(r1, r2)
+            s1, s2 = s1.cpu().numpy(), s2.cpu().numpy()
+            flags = int(s2[6]) & 0xFFFF
+            sel = [1, 3, 4, 5, 7] if metric == "pcc" else [5, 7]
+            assert np.array_equal(s1[sel], s2[sel]), (metric, s1, s2)
+            if metric == "pcc" and not (flags & 3):
+                assert np.array_equal(s1[[0, 2]], s2[[0, 2]])
 
 
 @pytest.mark.parametrize("strict", [False, True])
@@ -132,6 +157,7 @@ def test_algorithms_match_reference(qa, name, strict):
         params = dict(m["params"])
         if m["algo"] == "mixed-tile-greedy":
             params["strict_sums"] = strict
+            params["sequential_chain"] = strict      # strict run = NumPy-order sums + one-thread chain
         elif strict:
             continue
         res = ca.create_algorithm(m["algo"], params).run(x, G.FORMATS, ca.quantizer.Quantizer("emulation"), None)[0]
