@@ -565,6 +565,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     if (tid < QA_NFMT) cnt_sh[tid] = tid == base ? nt : 0;
     __syncthreads();
 
+    const long long t_start = clock64();
     // ---- (1) initial sums, sequentially rounded in tile order ------------------------------
     Consts c;
     c.n = numel; c.thr = thr; c.metric = metric; c.sx = 0.0; c.sx2 = 0.0;
@@ -595,6 +596,8 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     Pcg g;
     g.load(rng);
     unsigned chain_rounds = 0;
+    long long t_mark = clock64(), cyc_init = 0, cyc_perm = 0, cyc_chain = 0;
+    cyc_init = t_mark - t_start;
 
     for (int fi = 0; fi < ord.n; ++fi) {
         const int fmt = ord.fmt[fi];
@@ -613,7 +616,10 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         if (m == 0) break;
         const bool base_pass = (fmt == base) && (fi == 0);
         // ---- (2) visiting order ----------------------------------------------------------
+        t_mark = clock64();
         permutation_par(g, m, w.cand, w.order, w, !base_pass, sh);
+        cyc_perm += clock64() - t_mark;
+        t_mark = clock64();
         if (base_pass) {
             // every candidate already has this format: the state cannot change, so all of them
             // see the same test (mixed_tile_greedy.py:238-241)
@@ -740,6 +746,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             pos += valid;
             __syncthreads();
         }
+        cyc_chain += clock64() - t_mark;
     }
     if (tid == 0) {
         g.store(rng);
@@ -747,6 +754,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[0] = c.sx; state[1] = c.sx2; state[2] = S[0]; state[3] = S[1]; state[4] = S[2]; state[5] = S[3];
         state[6] = (double)degraded + 65536.0 * (double)chain_rounds;
         state[7] = is_pcc ? pcc_value_par(c, S[0], S[1], S[2], S[3]) : (numel != 0.0 ? __ddiv_rn(S[3], numel) : 0.0);
+        state[8] = (double)cyc_init; state[9] = (double)cyc_perm; state[10] = (double)cyc_chain;   // SM cycles per phase
     }
 }
 
