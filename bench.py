@@ -270,8 +270,8 @@ def main() -> None:
     kernels = [
         {"kernel": "stats_fast_kernel", "ms_per_step": ms_stats, "launches_per_step": len(batch.slots),
          "alg_bytes_per_step": alg_stats, "achieved_gbs": alg_stats / (ms_stats * 1e-3) / 1e9},
-        {"kernel": "greedy_par_kernel+assignment_sums_kernel", "ms_per_step": ms_assign,
-         "launches_per_step": 2 * len(batch.slots), "alg_bytes_per_step": alg_assign,
+        {"kernel": "greedy_par_kernel", "ms_per_step": ms_assign,
+         "launches_per_step": len(batch.slots), "alg_bytes_per_step": alg_assign,
          "achieved_gbs": alg_assign / (ms_assign * 1e-3) / 1e9},
     ]
     dom = max(kernels, key=lambda k: k["ms_per_step"])

@@ -43,7 +43,7 @@ class GreedyBatch:
             })
         self._rng0 = rng0
         self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
-        self.launches_per_step = 3 * len(self.slots)   # tile_stats + greedy + assignment_sums per tensor
+        self.launches_per_step = (3 if metric == "atol" else 2) * len(self.slots)   # tile_stats + greedy (+ sums) per tensor
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
@@ -69,8 +69,9 @@ class GreedyBatch:
                      METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
                      slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
                      slot["state"].data_ptr(), slot["work"].data_ptr(), sp), "qa_greedy_assign")
-            check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
-                                       slot["sums"].data_ptr(), sp), "qa_assignment_sums")
+            if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
+                check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
+                                           slot["sums"].data_ptr(), sp), "qa_assignment_sums")
 
     def run(self, stats: bool = True, assign: bool = True) -> None:
         """Enqueue one pass over every tensor; returns immediately (no host sync)."""
@@ -104,12 +105,15 @@ class GreedyBatch:
         packs = []
         for s in self.slots:
             packs.append((s["assignment"].to("cpu", non_blocking=True), s["counts"].to("cpu", non_blocking=True),
-                          s["sums"].to("cpu", non_blocking=True)))
+                          (s["sums"] if self.metric == "atol" else s["state"]).to("cpu", non_blocking=True)))
         torch.cuda.current_stream(self.device).synchronize()
         for s, (a, c, sums) in zip(self.slots, packs):
             counts = {f: int(c[i]) for i, f in enumerate(MIXED)}
+            v = sums.numpy()
+            if self.metric != "atol":      # state = {sx, sx2, sy, sy2, sxy, sabs, flags, value, cycles x3, max|x-y|, ...}
+                v = np.array([v[0], v[1], v[2], v[3], v[4], v[5], v[11]])
             out.append({"assignment": a.numpy().reshape(-(-s["rows"] // 32), -(-s["cols"] // 32)), "counts": counts,
-                        "metrics": engine.metrics_from_sums(sums.numpy(), s["numel"])})
+                        "metrics": engine.metrics_from_sums(v, s["numel"]), "state": sums.numpy().copy()})
         return out
 
     def d2h_bytes(self) -> int:

@@ -1,39 +1,45 @@
-// Parallel, bit-faithful greedy assignment: one 1024-thread block per tensor.
+// Parallel, bit-faithful greedy assignment: one thread-block CLUSTER per tensor.
 //
 // The reference's greedy (mixed_tile_greedy.py:135-346) is three sequential chains:
 //   (1) sequential float64 accumulation of the per-tile sums in tile order            (:165-170)
 //   (2) numpy Generator.permutation of the candidate tiles, once per format           (:228-231)
 //   (3) the accept/reject chain: cand = S + (new - old); accept iff metric(cand) passes (:234-346)
-// All three are reproduced here with the same results as a one-thread loop, in parallel:
+// All three are reproduced with the results of a one-thread loop, in parallel, by up to 16 CTAs
+// of a cluster that exchange scan totals through distributed shared memory:
 //
 //  * Sequentially rounded float64 sums.  While a running sum S stays in one binade its ulp q is
 //    fixed and S is an integer multiple m*q; adding t = (a + f)*q (a integer, 0 <= f < 1) gives
 //    m + a rounded to nearest - up if f > 1/2, down if f < 1/2, and to the even neighbour if
-//    f == 1/2.  The increment therefore depends on the running state only through the parity of
-//    m at exact ties, so a chunk of additions composes as pairs (increment if m even, increment
-//    if m odd): an associative operator, i.e. a block-wide prefix scan over int64 pairs.  The
-//    first element that leaves the binade [2^52, 2^53) q is itself still exact (it is evaluated
-//    with a real float64 add from the exact state before it); the chunk is cut after it and the
-//    next chunk starts with the new ulp.
+//    f == 1/2.  The increment depends on the running state only through the parity of m at exact
+//    ties, so a chunk of additions composes as pairs (increment if m even, increment if m odd):
+//    an associative operator, i.e. a prefix scan over int64 pairs.  The first element that leaves
+//    the binade [2^52, 2^53) q is itself still exact (it is a real float64 add from the exact
+//    state before it); the chunk is cut after it and the next chunk starts with the new ulp.
 //  * Decisions.  Within a chunk the accept flags F are guessed, the exact states before every
 //    element follow from the masked scan, every decision D is re-evaluated in parallel with the
-//    reference's float64 formula, and F is corrected from the first mismatch on; the fixed
-//    point is the sequential result.  (Typical passes are runs of accepts followed by runs of
-//    rejects, so this converges in a couple of rounds.)
+//    reference's float64 formula (behind an error-bounded multiplication-only filter), and F is
+//    corrected from the first mismatch on; the fixed point is the sequential result.
 //  * numpy permutation.  The 32-bit draw stream of PCG64 is generated in parallel by jumping the
-//    LCG; the masked-rejection acceptance (draw & mask <= i, i decreasing with every accept) is
-//    resolved per 8192-draw round by alternating lower/upper bounds on the accept count until
-//    they meet; the Fisher-Yates swap sequence is then applied in parallel by following, for
-//    every step, the chain of earlier steps that last wrote the position it reads.
+//    LCG; the masked-rejection acceptance (draw & mask(i) <= i, i decreasing with every accept) is
+//    a fixed point of  c = prefix_sum(accepts(c))  over per-thread accept counts; the Fisher-Yates
+//    swap sequence is then applied in parallel by following, for every step, the chain of earlier
+//    steps that last wrote the position it reads.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "qa_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace qa {
 
-constexpr int GT = 1024;          // threads per block
+constexpr int GT = 512;           // threads per CTA
 constexpr int NW = GT / 32;
+constexpr int MAXR = 16;          // largest cluster
 constexpr int DPT = 8;            // draws per thread per round (4 LCG outputs)
 constexpr int EPT = 2;            // chain elements per thread per chunk
-constexpr int CH = GT * EPT;      // chunk length
+constexpr int SEQ_TAIL = 96;      // last Fisher-Yates steps are drawn by one thread
 constexpr long long M_LO = 1ll << 52, M_HI = 1ll << 53;
 
 struct ParOrder {
@@ -50,21 +56,46 @@ struct ParWork {
     int32_t* bucket;  // [n]
     int32_t* succ;    // [n]
     int32_t* parent;  // [n]
+    double* dbuf;     // [4][n]  per-candidate deltas in visiting order
     uint8_t* fixed;   // [n]
+};
+
+struct P2 {          // increment of m if the incoming m is even / odd
+    long long d0, d1;
 };
 
 struct Sh {
     int i32[40];
     long long i64[NW * 6 * 2 + 16];
     double f64[16];
-    u128 rs;            // LCG state at output index rk
-    unsigned long long rk;
-    unsigned long long pnext;
-    int flag;
+    // cluster exchange (double buffered; written by remote CTAs through DSMEM)
+    int xi[2][MAXR];
+    long long xl[2][MAXR][12];
+    double xd[2][MAXR];
+    int cnt[QA_NFMT];
+};
+
+struct Coop {
+    Sh& sh;
+    cg::cluster_group cl;
+    unsigned rank, nr;
+    int gtid, gth;       // cluster-wide thread id / thread count
+    unsigned par;        // exchange parity (uniform)
+    __device__ Coop(Sh& s) : sh(s), cl(cg::this_cluster()) {
+        rank = cl.block_rank();
+        nr = cl.num_blocks();
+        gtid = (int)rank * GT + (int)threadIdx.x;
+        gth = (int)nr * GT;
+        par = 0;
+    }
+    __device__ __forceinline__ void sync() {
+        if (nr == 1) __syncthreads();
+        else cl.sync();
+    }
 };
 
 // ---------------------------------------------------------------------------------------------
-// block-wide helpers
+// block / cluster collectives (every thread of the cluster calls them, values come back uniform)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int block_scan_excl(int v, int& total, Sh& sh) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -76,53 +107,105 @@ __device__ __forceinline__ int block_scan_excl(int v, int& total, Sh& sh) {
     }
     if (lane == 31) sh.i32[w] = inc;
     __syncthreads();
-    if (w == 0) {
-        const int x = sh.i32[lane];
-        int xi = x;
+    int pre = 0, tot = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xFFFFFFFFu, xi, o);
-            if (lane >= o) xi += y;
-        }
-        sh.i32[lane] = xi - x;
-        if (lane == 31) sh.i32[32] = xi;
+    for (int i = 0; i < NW; ++i) {
+        const int x = sh.i32[i];
+        tot += x;
+        if (i < w) pre += x;
+    }
+    total = tot;
+    __syncthreads();
+    return pre + inc - v;
+}
+
+__device__ __forceinline__ int c_scan_excl(Coop& c, int v, int& total) {
+    int bt;
+    const int ex = block_scan_excl(v, bt, c.sh);
+    if (c.nr == 1) { total = bt; return ex; }
+    const unsigned b = c.par++ & 1u;
+    if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = bt;
+    c.cl.sync();
+    int base = 0, tot = 0;
+    for (unsigned r = 0; r < c.nr; ++r) {
+        const int x = c.sh.xi[b][r];
+        tot += x;
+        if (r < c.rank) base += x;
+    }
+    total = tot;
+    return base + ex;
+}
+
+__device__ __forceinline__ int c_min(Coop& c, int v) {
+    v = __reduce_min_sync(0xFFFFFFFFu, v);
+    if ((threadIdx.x & 31) == 0) c.sh.i32[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = c.sh.i32[0];
+#pragma unroll
+    for (int i = 1; i < NW; ++i) r = min(r, c.sh.i32[i]);
+    __syncthreads();
+    if (c.nr == 1) return r;
+    const unsigned b = c.par++ & 1u;
+    if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = r;
+    c.cl.sync();
+    int m = c.sh.xi[b][0];
+    for (unsigned q = 1; q < c.nr; ++q) m = min(m, c.sh.xi[b][q]);
+    return m;
+}
+
+__device__ __forceinline__ bool c_any(Coop& c, bool p) {
+    const int blk = __syncthreads_or(p ? 1 : 0);
+    if (c.nr == 1) return blk != 0;
+    const unsigned b = c.par++ & 1u;
+    if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = blk;
+    c.cl.sync();
+    int m = 0;
+    for (unsigned q = 0; q < c.nr; ++q) m |= c.sh.xi[b][q];
+    return m != 0;
+}
+
+// deterministic cluster-wide float64 sum / max (fixed tree: lanes, warps in order, CTAs in order)
+template <bool MAX>
+__device__ __forceinline__ double c_reduce_d(Coop& c, double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double y = __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v), o),
+                                          __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v), o));
+        v = MAX ? fmax(v, y) : v + y;
+    }
+    if ((threadIdx.x & 31) == 0) c.sh.i64[threadIdx.x >> 5] = __double_as_longlong(v);
+    __syncthreads();
+    double r = __longlong_as_double(c.sh.i64[0]);
+    for (int i = 1; i < NW; ++i) {
+        const double y = __longlong_as_double(c.sh.i64[i]);
+        r = MAX ? fmax(r, y) : r + y;
     }
     __syncthreads();
-    const int res = sh.i32[w] + inc - v;
-    total = sh.i32[32];
-    __syncthreads();
-    return res;
+    if (c.nr == 1) return r;
+    const unsigned b = c.par++ & 1u;
+    if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xd[b][c.rank], threadIdx.x) = r;
+    c.cl.sync();
+    double t = c.sh.xd[b][0];
+    for (unsigned q = 1; q < c.nr; ++q) t = MAX ? fmax(t, c.sh.xd[b][q]) : t + c.sh.xd[b][q];
+    return t;
 }
 
-__device__ __forceinline__ int block_min(int v, Sh& sh) {
-    v = __reduce_min_sync(0xFFFFFFFFu, v);
-    if ((threadIdx.x & 31) == 0) sh.i32[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int r = sh.i32[threadIdx.x & 31];
-    r = __reduce_min_sync(0xFFFFFFFFu, r);
-    __syncthreads();
-    return r;
-}
-
-__device__ __forceinline__ double block_sum_d(double v, Sh& sh) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1)
-        v += __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v), o),
-                              __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v), o));
-    if ((threadIdx.x & 31) == 0) sh.f64[0] = 0.0, sh.i64[threadIdx.x >> 5] = __double_as_longlong(v);
-    __syncthreads();
-    double r = 0.0;
-    for (int i = 0; i < NW; ++i) r += __longlong_as_double(sh.i64[i]);
-    __syncthreads();
-    return r;
+// One thread of the cluster (owner) publishes n <= 8 doubles to every CTA; all threads read them back.
+__device__ __forceinline__ void c_bcast_d(Coop& c, bool owner, const double* vals, int n, double* out) {
+    const unsigned b = c.par++ & 1u;
+    if (owner) {
+        for (unsigned r = 0; r < c.nr; ++r) {
+            double* dst = c.nr == 1 ? &c.sh.xd[b][0] : c.cl.map_shared_rank(&c.sh.xd[b][0], r);
+            for (int i = 0; i < n; ++i) dst[i] = vals[i];
+        }
+    }
+    c.sync();
+    for (int i = 0; i < n; ++i) out[i] = c.sh.xd[b][i];
 }
 
 // ---------------------------------------------------------------------------------------------
 // sequentially-rounded float64 accumulation as a scan
 // ---------------------------------------------------------------------------------------------
-struct P2 {          // increment of m if the incoming m is even / odd
-    long long d0, d1;
-};
 __device__ __forceinline__ P2 p2_then(P2 a, P2 b) {   // apply a, then b
     P2 r;
     r.d0 = a.d0 + ((a.d0 & 1ll) ? b.d1 : b.d0);
@@ -163,11 +246,20 @@ __device__ __forceinline__ bool classify(const Grid& g, double t, P2& out) {
 }
 __device__ __forceinline__ long long m_after(const Grid& g, P2 p) { return g.m0 + ((g.m0 & 1ll) ? p.d1 : p.d0); }
 __device__ __forceinline__ double s_of(const Grid& g, long long m) { return g.sign * ((double)m * g.q); }
+__device__ __forceinline__ bool in_binade(long long m) { return m >= M_LO && m < M_HI; }
 
-// exclusive block scan of NS P2 streams, EPT elements per thread (element order = thread-major);
-// element k of a thread takes part iff bit k of `on` is set.
+__device__ __forceinline__ P2 shfl_up_p2(P2 v, int o) {
+    P2 y;
+    y.d0 = __shfl_up_sync(0xFFFFFFFFu, v.d0, o);
+    y.d1 = __shfl_up_sync(0xFFFFFFFFu, v.d1, o);
+    return y;
+}
+
+// Exclusive cluster-wide scan of NS P2 streams, EPT elements per thread (element order = cluster
+// thread-major); element k of a thread takes part iff bit k of `on` is set.
 template <int NS>
-__device__ __forceinline__ void scan_p2(const P2 (&cls)[NS][EPT], unsigned on, P2 (&ex)[NS][EPT], Sh& sh) {
+__device__ __forceinline__ void scan_p2(Coop& c, const P2 (&cls)[NS][EPT], unsigned on, P2 (&ex)[NS][EPT]) {
+    Sh& sh = c.sh;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     P2 inc[NS];
 #pragma unroll
@@ -181,57 +273,120 @@ __device__ __forceinline__ void scan_p2(const P2 (&cls)[NS][EPT], unsigned on, P
         inc[s] = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            P2 y;
-            y.d0 = __shfl_up_sync(0xFFFFFFFFu, inc[s].d0, o);
-            y.d1 = __shfl_up_sync(0xFFFFFFFFu, inc[s].d1, o);
+            const P2 y = shfl_up_p2(inc[s], o);
             if (lane >= o) inc[s] = p2_then(y, inc[s]);
         }
         if (lane == 31) { sh.i64[(w * NS + s) * 2] = inc[s].d0; sh.i64[(w * NS + s) * 2 + 1] = inc[s].d1; }
     }
     __syncthreads();
+    // warp 0 turns the NW warp totals into exclusive prefixes (+ the CTA total in slot NW)
+    if (w == 0) {
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        P2 pre{0, 0};
-        for (int i = 0; i < w; ++i) {                    // totals of the warps before this one
-            P2 t;
-            t.d0 = sh.i64[(i * NS + s) * 2];
-            t.d1 = sh.i64[(i * NS + s) * 2 + 1];
-            pre = p2_then(pre, t);
+        for (int s = 0; s < NS; ++s) {
+            P2 t{0, 0};
+            if (lane < NW) { t.d0 = sh.i64[(lane * NS + s) * 2]; t.d1 = sh.i64[(lane * NS + s) * 2 + 1]; }
+            P2 ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const P2 y = shfl_up_p2(ti, o);
+                if (lane >= o) ti = p2_then(y, ti);
+            }
+            P2 te = shfl_up_p2(ti, 1);
+            if (lane == 0) te = P2{0, 0};
+            __syncwarp();
+            if (lane < NW) { sh.i64[(lane * NS + s) * 2] = te.d0; sh.i64[(lane * NS + s) * 2 + 1] = te.d1; }
+            if (lane == NW - 1) { sh.i64[(NW * NS + s) * 2] = ti.d0; sh.i64[(NW * NS + s) * 2 + 1] = ti.d1; }
         }
-        P2 lanes_before;
-        lanes_before.d0 = __shfl_up_sync(0xFFFFFFFFu, inc[s].d0, 1);
-        lanes_before.d1 = __shfl_up_sync(0xFFFFFFFFu, inc[s].d1, 1);
-        if (lane == 0) lanes_before = P2{0, 0};
-        pre = p2_then(pre, lanes_before);
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) ex[s][k] = p2_then(pre, ex[s][k]);
     }
     __syncthreads();
+    P2 pre[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        pre[s].d0 = sh.i64[(w * NS + s) * 2];
+        pre[s].d1 = sh.i64[(w * NS + s) * 2 + 1];
+        P2 lanes_before = shfl_up_p2(inc[s], 1);
+        if (lane == 0) lanes_before = P2{0, 0};
+        pre[s] = p2_then(pre[s], lanes_before);
+    }
+    if (c.nr > 1) {
+        const unsigned b = c.par++ & 1u;
+        if (threadIdx.x < c.nr) {
+            long long* dst = c.cl.map_shared_rank(&sh.xl[b][c.rank][0], threadIdx.x);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) { dst[2 * s] = sh.i64[(NW * NS + s) * 2]; dst[2 * s + 1] = sh.i64[(NW * NS + s) * 2 + 1]; }
+        }
+        c.cl.sync();
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            P2 cp{0, 0};
+            for (unsigned r = 0; r < c.rank; ++r) cp = p2_then(cp, P2{sh.xl[b][r][2 * s], sh.xl[b][r][2 * s + 1]});
+            pre[s] = p2_then(cp, pre[s]);
+        }
+    } else {
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) ex[s][k] = p2_then(pre[s], ex[s][k]);
 }
 
 // ---------------------------------------------------------------------------------------------
-// metric evaluation (reference formula, float64, no contraction)
+// metric evaluation
 // ---------------------------------------------------------------------------------------------
 struct Consts {
     double n, sx, sx2, thr;
     int metric;
+    // derived (pcc): reference intermediates and the filter's constants
+    double mx, nmx, am2, inv_n, K;
+    bool filter_ok;
 };
+__device__ __forceinline__ void consts_finish(Consts& c) {
+    c.mx = c.n != 0.0 ? __ddiv_rn(c.sx, c.n) : 0.0;
+    c.nmx = __dmul_rn(c.n, c.mx);
+    double am2 = __dsub_rn(c.sx2, __dmul_rn(c.nmx, c.mx));
+    if (am2 < 0.0) am2 = 0.0;
+    c.am2 = am2;
+    c.inv_n = c.n != 0.0 ? 1.0 / c.n : 0.0;
+    c.K = c.thr * c.thr * am2;
+    c.filter_ok = c.metric == QA_METRIC_PCC && c.thr > 0.0 && am2 > 0.0 && c.n > 0.0 && isfinite(c.K);
+}
+// mixed_tile_greedy.py:176-190 in Python-float order (no contraction); mx, n*mx and am2 are loop invariants
 __device__ __forceinline__ double pcc_value_par(const Consts& c, double sy, double sy2, double sxy, double sabs) {
     if (c.n == 0.0) return 1.0;
-    const double mx = __ddiv_rn(c.sx, c.n);
     const double my = __ddiv_rn(sy, c.n);
-    double am2 = __dsub_rn(c.sx2, __dmul_rn(__dmul_rn(c.n, mx), mx));
     double bm2 = __dsub_rn(sy2, __dmul_rn(__dmul_rn(c.n, my), my));
-    if (am2 < 0.0) am2 = 0.0;
     if (bm2 < 0.0) bm2 = 0.0;
-    const double den = __dsqrt_rn(__dmul_rn(am2, bm2));
+    const double den = __dsqrt_rn(__dmul_rn(c.am2, bm2));
     if (den == 0.0) return sabs == 0.0 ? 1.0 : 0.0;
-    return __ddiv_rn(__dsub_rn(sxy, __dmul_rn(__dmul_rn(c.n, mx), my)), den);
+    return __ddiv_rn(__dsub_rn(sxy, __dmul_rn(c.nmx, my)), den);
 }
 __device__ __forceinline__ bool good_par(const Consts& c, const double (&S)[4]) {
-    if (c.metric == QA_METRIC_PCC) return pcc_value_par(c, S[0], S[1], S[2], S[3]) >= c.thr;
-    const double v = c.n != 0.0 ? __ddiv_rn(S[3], c.n) : 0.0;
-    return v <= c.thr;
+    if (c.metric != QA_METRIC_PCC) {
+        const double v = c.n != 0.0 ? __ddiv_rn(S[3], c.n) : 0.0;
+        return v <= c.thr;
+    }
+    if (c.filter_ok) {
+        // value >= thr  <=>  num >= thr*den  <=>  num > 0 and num^2 >= thr^2 * am2 * bm2.
+        // Evaluate both sides with multiplications only and decide when the gap exceeds a bound on
+        // every rounding involved (here and in the reference formula): 512 ulp of the terms.
+        const double my = S[0] * c.inv_n;
+        const double t1 = c.nmx * my;
+        const double num = S[2] - t1;
+        const double t2 = (c.n * my) * my;
+        const double bm2 = S[1] - t2;
+        const double enum_ = 5.7e-14 * (fabs(S[2]) + fabs(t1));            // bound on the error of num
+        const double ebm2 = 5.7e-14 * (fabs(S[1]) + fabs(t2));             // ... and of bm2
+        if (bm2 > ebm2) {
+            if (num < -enum_) return false;                                 // certainly negative correlation
+            if (num > enum_) {
+                const double gap = num * num - c.K * bm2;
+                const double tol = 2.0 * enum_ * fabs(num) + c.K * ebm2 + 5.7e-14 * (num * num + c.K * bm2);
+                if (fabs(gap) > tol) return gap > 0.0;
+            }
+        }
+    }
+    return pcc_value_par(c, S[0], S[1], S[2], S[3]) >= c.thr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -257,159 +412,157 @@ __device__ void lcg_jump_consts(u128 inc, uint64_t delta, u128& am, u128& ap) {
     }
 }
 
-// count accepts among this thread's DPT draws given the accept count `c` before them
-__device__ __forceinline__ int local_accepts(const uint32_t (&v)[DPT], uint32_t validmask, int c, int T, int L) {
+// accepts among this thread's DPT raw draws when `c` accepts precede them: step i = T - c draws until
+// (raw & mask(i)) <= i (numpy random_interval); at most L accepts in total.
+__device__ __forceinline__ int local_accepts(const uint32_t (&raw)[DPT], uint32_t validmask, int c, int T, int L) {
     int a = 0;
 #pragma unroll
     for (int j = 0; j < DPT; ++j) {
-        const bool ok = ((validmask >> j) & 1u) && (c + a < L) && ((int)v[j] <= T - (c + a));
+        const int i = T - (c + a);
+        const uint32_t mask = i > 0 ? (0xFFFFFFFFu >> __clz((uint32_t)i)) : 0u;
+        const bool ok = ((validmask >> j) & 1u) && (c + a < L) && ((raw[j] & mask) <= (uint32_t)i);
         a += ok ? 1 : 0;
     }
     return a;
 }
 
-// Generates numpy's permutation(m) from the stream in `g` (uniform across the block; every thread
-// holds the same copy), writes out[k] = cand ? cand[perm[k]] : perm[k].  apply == false only advances
+// Generates numpy's permutation(m) from the stream in `g` (uniform: every thread of the cluster holds
+// the same copy) and writes out[k] = cand ? cand[perm[k]] : perm[k].  apply == false only advances
 // the stream (the visiting order is irrelevant when the running state cannot change).
-__device__ void permutation_par(Pcg& g, int m, const int32_t* cand, int32_t* out, const ParWork& w, bool apply, Sh& sh) {
+__device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int32_t* out, const ParWork& w, bool apply) {
     const int tid = threadIdx.x;
     if (m <= 1) {
-        if (m == 1 && apply && tid == 0) out[0] = cand ? cand[0] : 0;
-        __syncthreads();
+        if (m == 1 && apply && c.gtid == 0) out[0] = cand ? cand[0] : 0;
+        c.sync();
         return;
     }
-    // per-thread jump constants for 4*tid LCG steps
-    u128 am, ap;
-    lcg_jump_consts(g.inc, 4ull * (uint64_t)tid, am, ap);
-    if (tid == 0) {
-        sh.rs = g.s;                 // state at output index rk (out_rk = pcg_out(rs)); out_0.hi == buffered half
-        sh.rk = 0ull;
-        sh.pnext = g.has32 ? 1ull : 2ull;
-    }
-    __syncthreads();
+    // jump constants: 4*gtid LCG steps (this thread's offset in a round) and one full round
+    u128 am, ap, rm, rp;
+    lcg_jump_consts(g.inc, 4ull * (uint64_t)c.gtid, am, ap);
+    lcg_jump_consts(g.inc, 4ull * (uint64_t)c.gth, rm, rp);
+    // uniform stream cursor: rs = LCG state at output index rk (out_k = pcg_out(state_k); the buffered
+    // half, if any, is the high half of out_0); pnext = position (2*k + half) of the next unconsumed draw
+    u128 rs = g.s;
+    unsigned long long rk = 0ull, pnext = g.has32 ? 1ull : 2ull;
     int i_cur = m - 1;
-    const int SEQ_TAIL = 96;
     while (i_cur > SEQ_TAIL) {
-        const uint32_t mask = 0xFFFFFFFFu >> __clz((uint32_t)i_cur);
-        const int seg_lo = (int)(mask >> 1) + 1;
-        const int L = i_cur - max(seg_lo, SEQ_TAIL + 1) + 1;      // accepts wanted in this segment
-        // advance the shared base to output index kb = pnext >> 1
-        const unsigned long long pnext = sh.pnext;
+        const int L = i_cur - SEQ_TAIL;                      // accepts still wanted from the parallel part
         const unsigned long long kb = pnext >> 1;
-        if (tid == 0 && kb != sh.rk) {
-            u128 a2, p2;
-            lcg_jump_consts(g.inc, kb - sh.rk, a2, p2);
-            sh.rs = add128(mul128(a2, sh.rs), p2);
-            sh.rk = kb;
+        if (kb != rk) {
+            if (kb - rk == 4ull * (unsigned long long)c.gth) rs = add128(mul128(rm, rs), rp);
+            else { u128 a2, p2; lcg_jump_consts(g.inc, kb - rk, a2, p2); rs = add128(mul128(a2, rs), p2); }
+            rk = kb;
         }
-        __syncthreads();
-        // this thread's 4 outputs: indices kb + 4 tid + j
-        u128 s = add128(mul128(am, sh.rs), ap);
-        uint32_t v[DPT];
-        uint32_t validmask = 0;
+        u128 s = add128(mul128(am, rs), ap);                 // state at output index kb + 4*gtid
+        uint32_t raw[DPT];
 #pragma unroll
         for (int j = 0; j < DPT / 2; ++j) {
             const uint64_t o = pcg_out(s);
-            v[2 * j] = (uint32_t)o & mask;
-            v[2 * j + 1] = (uint32_t)(o >> 32) & mask;
+            raw[2 * j] = (uint32_t)o;
+            raw[2 * j + 1] = (uint32_t)(o >> 32);
             s = pcg_step(s, g.inc);
         }
-        const unsigned long long p0 = 2ull * (kb + 4ull * (unsigned long long)tid);
+        const unsigned long long p0 = 2ull * (kb + 4ull * (unsigned long long)c.gtid);
+        uint32_t validmask = 0;
 #pragma unroll
         for (int j = 0; j < DPT; ++j)
             if (p0 + j >= pnext) validmask |= 1u << j;
-        // resolve the accept counts by alternating bounds
-        int c_lo = 0, a_hi = 0, a_lo = 0, total = 0;
-        for (int it = 0; it < 64; ++it) {
-            a_hi = local_accepts(v, validmask, c_lo, i_cur, L);
-            const int c_hi = block_scan_excl(a_hi, total, sh);
-            a_lo = local_accepts(v, validmask, c_hi, i_cur, L);
-            c_lo = block_scan_excl(a_lo, total, sh);
-            const int a_chk = local_accepts(v, validmask, c_lo, i_cur, L);
-            const int diff = __syncthreads_or(a_chk != a_lo);
-            if (!diff) break;
+        // fixed point of c_in = exclusive_prefix(accepts(c_in)); thread 0 is right from the start and
+        // every sweep fixes at least one more thread (typically all of them within ~10 sweeps)
+        int c_in = 0, total = 0, a = local_accepts(raw, validmask, 0, i_cur, L);
+        for (;;) {
+            const int c_new = c_scan_excl(c, a, total);
+            const int a_new = local_accepts(raw, validmask, c_new, i_cur, L);
+            const bool changed = (a_new != a) || (c_new != c_in);
+            a = a_new;
+            c_in = c_new;
+            if (!c_any(c, changed)) break;
         }
-        // total = accepts in this round with exact c_lo per thread
+        // write j for the steps this thread resolved; find the draw that supplied the L-th accept
+        int done_off = 0x7FFFFFFF;
         {
-            int c = c_lo;
-            unsigned long long last_pos = ~0ull;
+            int cc = c_in;
 #pragma unroll
             for (int j = 0; j < DPT; ++j) {
-                const bool ok = ((validmask >> j) & 1u) && (c < L) && ((int)v[j] <= i_cur - c);
+                const int i = i_cur - cc;
+                const uint32_t mask = i > 0 ? (0xFFFFFFFFu >> __clz((uint32_t)i)) : 0u;
+                const bool ok = ((validmask >> j) & 1u) && (cc < L) && ((raw[j] & mask) <= (uint32_t)i);
                 if (ok) {
-                    w.jarr[i_cur - c] = (int32_t)v[j];
-                    ++c;
-                    if (c == L) last_pos = p0 + j;      // the draw that completes the segment
+                    w.jarr[i] = (int32_t)(raw[j] & mask);
+                    ++cc;
+                    if (cc == L) done_off = c.gtid * DPT + j;
                 }
             }
-            if (last_pos != ~0ull) sh.pnext = last_pos + 1ull;
         }
-        __syncthreads();
-        if (total < L) {            // segment not finished: every draw of the round was consumed
-            if (tid == 0) sh.pnext = 2ull * (kb + 4ull * GT);
+        if (total >= L) {
+            const int off = c_min(c, done_off);
+            pnext = 2ull * kb + (unsigned long long)off + 1ull;
+        } else {
+            pnext = 2ull * (kb + 4ull * (unsigned long long)c.gth);      // every draw of the round was consumed
         }
         i_cur -= total;
-        __syncthreads();
     }
-    // sequential tail (and stream hand-back) on thread 0
+    // sequential tail and stream hand-back: computed redundantly (and identically) by one thread per CTA
     if (tid == 0) {
-        const unsigned long long pnext = sh.pnext;
         const unsigned long long klast = (pnext - 1ull) >> 1;
         u128 a2, p2;
-        lcg_jump_consts(g.inc, klast - sh.rk, a2, p2);
-        const u128 s = add128(mul128(a2, sh.rs), p2);
+        lcg_jump_consts(g.inc, klast - rk, a2, p2);
+        const u128 s = add128(mul128(a2, rs), p2);
         Pcg t;
         t.inc = g.inc;
         t.s = s;
-        t.has32 = ((pnext - 1ull) & 1ull) == 0ull ? 1u : 0u;
+        t.has32 = ((pnext - 1ull) & 1ull) == 0ull ? 1u : 0u;   // last consumed draw was a low half
         t.buf32 = (uint32_t)(pcg_out(s) >> 32);
-        if (pnext == 2ull && !g.has32) { t.s = g.s; t.has32 = 0; t.buf32 = g.buf32; }   // nothing consumed yet
-        if (pnext == 1ull) { t.s = g.s; t.has32 = 1; t.buf32 = g.buf32; }
-        for (int i = i_cur; i >= 1; --i) w.jarr[i] = (int32_t)t.interval((uint32_t)i);
-        sh.rs = t.s;
-        sh.i32[34] = (int)t.has32;
-        sh.i32[35] = (int)t.buf32;
+        for (int i = i_cur; i >= 1; --i) {
+            const int32_t j = (int32_t)t.interval((uint32_t)i);
+            if (c.rank == 0) w.jarr[i] = j;
+        }
+        c.sh.i64[0] = (long long)t.s.hi;
+        c.sh.i64[1] = (long long)t.s.lo;
+        c.sh.i32[34] = (int)t.has32;
+        c.sh.i32[35] = (int)t.buf32;
     }
     __syncthreads();
-    g.s = sh.rs;
-    g.has32 = (uint32_t)sh.i32[34];
-    g.buf32 = (uint32_t)sh.i32[35];
-    __syncthreads();
+    g.s.hi = (uint64_t)c.sh.i64[0];
+    g.s.lo = (uint64_t)c.sh.i64[1];
+    g.has32 = (uint32_t)c.sh.i32[34];
+    g.buf32 = (uint32_t)c.sh.i32[35];
+    c.sync();
     if (!apply) return;
 
     // ---- apply the swap sequence j[m-1..1] in parallel --------------------------------------
-    for (int p = tid; p < m; p += GT) w.cursor[p] = 0;
-    __syncthreads();
-    for (int i = 1 + tid; i < m; i += GT) atomicAdd(&w.cursor[w.jarr[i]], 1);
-    __syncthreads();
+    for (int p = c.gtid; p < m; p += c.gth) w.cursor[p] = 0;
+    c.sync();
+    for (int i = 1 + c.gtid; i < m; i += c.gth) atomicAdd(&w.cursor[w.jarr[i]], 1);
+    c.sync();
     {   // exclusive scan of the per-position counts -> off[], contiguous range per thread
-        const int per = (m + GT - 1) / GT;
-        const int b = min(m, tid * per), e = min(m, b + per);
+        const int per = (m + c.gth - 1) / c.gth;
+        const int b = min(m, c.gtid * per), e = min(m, b + per);
         int local = 0;
         for (int p = b; p < e; ++p) local += w.cursor[p];
         int total;
-        int run = block_scan_excl(local, total, sh);
+        int run = c_scan_excl(c, local, total);
         for (int p = b; p < e; ++p) {
-            const int c = w.cursor[p];
+            const int cnt = w.cursor[p];
             w.off[p] = run;
             w.cursor[p] = run;
-            run += c;
+            run += cnt;
         }
-        if (tid == 0) w.off[m] = total;
+        if (c.gtid == 0) w.off[m] = total;
     }
-    __syncthreads();
-    for (int i = 1 + tid; i < m; i += GT) {
+    c.sync();
+    for (int i = 1 + c.gtid; i < m; i += c.gth) {
         const int slot = atomicAdd(&w.cursor[w.jarr[i]], 1);
         w.bucket[slot] = i;
     }
-    __syncthreads();
-    for (int p = tid; p < m; p += GT) {
+    c.sync();
+    for (int p = c.gtid; p < m; p += c.gth) {
         const int b = w.off[p], e = w.off[p + 1];
         for (int a = b + 1; a < e; ++a) {          // insertion sort (buckets hold ~1 entry)
             const int key = w.bucket[a];
-            int c = a - 1;
-            while (c >= b && w.bucket[c] > key) { w.bucket[c + 1] = w.bucket[c]; --c; }
-            w.bucket[c + 1] = key;
+            int q = a - 1;
+            while (q >= b && w.bucket[q] > key) { w.bucket[q + 1] = w.bucket[q]; --q; }
+            w.bucket[q + 1] = key;
         }
         int par = -1;
         for (int a = b; a < e; ++a) {
@@ -417,10 +570,10 @@ __device__ void permutation_par(Pcg& g, int m, const int32_t* cand, int32_t* out
             w.succ[st] = a + 1 < e ? w.bucket[a + 1] : -1;
             if (par < 0 && st != p) par = st;
         }
-        w.parent[p] = par;       // first later step that writes position p
+        w.parent[p] = par;       // first later-executed step that writes position p
     }
-    __syncthreads();
-    for (int i = tid; i < m; i += GT) {
+    c.sync();
+    for (int i = c.gtid; i < m; i += c.gth) {
         // a[0] ends as the content of position 0 after all steps; a[i] (i >= 1) is what step i read
         const int start = i == 0 ? w.parent[0] : w.succ[i];
         int val;
@@ -432,28 +585,29 @@ __device__ void permutation_par(Pcg& g, int m, const int32_t* cand, int32_t* out
         }
         out[i] = cand ? cand[val] : val;
     }
-    __syncthreads();
+    c.sync();
 }
 
 __global__ void __launch_bounds__(GT) permutation_par_kernel(qa_pcg64* rng, int m, int32_t* out, ParWork w) {
     __shared__ Sh sh;
+    Coop c(sh);
     Pcg g;
     g.load(rng);
-    permutation_par(g, m, nullptr, out, w, true, sh);
-    if (threadIdx.x == 0) g.store(rng);
+    c.sync();                       // everyone has read the stream before rank 0 overwrites it
+    permutation_par(c, g, m, nullptr, out, w, true);
+    if (c.gtid == 0) g.store(rng);
 }
 
 // ---------------------------------------------------------------------------------------------
-// the greedy kernel
+// faithful sequential sums of table columns (tile order): S_k = fl(S_{k-1} + t_k)
 // ---------------------------------------------------------------------------------------------
-// Faithful sequential sum of table column(s) in tile order: S_k = fl(S_{k-1} + t_k).
-// The first HEAD elements (where a sum starting from zero changes binade at almost every step)
-// are added by one thread; the rest rides the scan.  A column whose running sum keeps leaving its
-// binade (a zero-mean random walk around a power of two) is finished with a plain tree sum after
-// MAX_EVENTS cuts and reported in `degraded` (bit per column).
+// The first HEAD elements (a sum starting from zero changes binade at almost every step) are added
+// by one thread; the rest rides the scan.  A column whose running sum keeps leaving its binade (a
+// zero-mean random walk) is finished with a plain tree sum after max_events cuts and flagged.
 template <int NC>
-__device__ void faithful_init_sums(const double* const (&col)[NC], int nt, double (&S)[NC], unsigned& degraded,
-                                   int max_events, Sh& sh) {
+__device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int nt, double (&S)[NC], unsigned& degraded,
+                                   int max_events) {
+    Sh& sh = c.sh;
     const int tid = threadIdx.x;
     constexpr int HEAD = 192;
     int events[NC];
@@ -473,8 +627,9 @@ __device__ void faithful_init_sums(const double* const (&col)[NC], int nt, doubl
 #pragma unroll
     for (int s = 0; s < NC; ++s) S[s] = sh.f64[s];
     __syncthreads();
+    const int CHc = c.gth * EPT;
     while (pos < nt) {
-        const int len = min(CH, nt - pos);
+        const int len = min(CHc, nt - pos);
         Grid g[NC];
         P2 cls[NC][EPT], ex[NC][EPT];
         double t[NC][EPT];
@@ -484,7 +639,7 @@ __device__ void faithful_init_sums(const double* const (&col)[NC], int nt, doubl
             g[s] = make_grid(S[s]);
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
-                const int idx = tid * EPT + k;
+                const int idx = c.gtid * EPT + k;
                 t[s][k] = idx < len ? col[s][pos + idx] : 0.0;
                 cls[s][k] = P2{0, 0};
                 if (idx < len && !((degraded >> s) & 1u)) {
@@ -492,57 +647,60 @@ __device__ void faithful_init_sums(const double* const (&col)[NC], int nt, doubl
                 }
             }
         }
-        bad = block_min(bad, sh);
+        bad = c_min(c, bad);
         unsigned on = 0;                                // elements before `bad` ride the scan
 #pragma unroll
         for (int k = 0; k < EPT; ++k)
-            if (tid * EPT + k < bad && tid * EPT + k < len) on |= 1u << k;
-        scan_p2<NC>(cls, on, ex, sh);
+            if (c.gtid * EPT + k < bad && c.gtid * EPT + k < len) on |= 1u << k;
+        scan_p2<NC>(c, cls, on, ex);
         int cut = min(bad, len - 1);                    // last element handled this round
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
             if ((degraded >> s) & 1u) continue;
 #pragma unroll
             for (int k = 0; k < EPT; ++k) {
-                if ((on >> k) & 1u) {
-                    const long long mi = m_after(g[s], p2_then(ex[s][k], cls[s][k]));
-                    if (g[s].q != 0.0 && (mi < M_LO || mi >= M_HI)) cut = min(cut, tid * EPT + k);
-                }
+                if (((on >> k) & 1u) && g[s].q != 0.0 && !in_binade(m_after(g[s], p2_then(ex[s][k], cls[s][k]))))
+                    cut = min(cut, c.gtid * EPT + k);
             }
         }
-        cut = block_min(cut, sh);
+        cut = c_min(c, cut);
         // state after element `cut` = fl(S_before(cut) + t_cut): a real add from the exact state before it
-        if (cut / EPT == tid) {
+        double nv[NC];
+        {
+            const bool owner = cut / EPT == c.gtid;
+            double vals[NC];
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                if (k != cut % EPT) continue;
+            for (int s = 0; s < NC; ++s) vals[s] = 0.0;
+            if (owner) {
 #pragma unroll
-                for (int s = 0; s < NC; ++s) {
-                    const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], ex[s][k])) : S[s];
-                    sh.f64[s] = __dadd_rn(before, t[s][k]);
+                for (int k = 0; k < EPT; ++k) {
+                    if (k != cut % EPT) continue;
+#pragma unroll
+                    for (int s = 0; s < NC; ++s) {
+                        const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], ex[s][k])) : S[s];
+                        vals[s] = __dadd_rn(before, t[s][k]);
+                    }
                 }
             }
+            c_bcast_d(c, owner, vals, NC, nv);
         }
-        __syncthreads();
         const bool cut_short = cut < len - 1;
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
             if ((degraded >> s) & 1u) continue;
-            const double nv = sh.f64[s];
             if (cut_short) {
-                const Grid gn = make_grid(nv);
+                const Grid gn = make_grid(nv[s]);
                 if (gn.q != g[s].q || g[s].q == 0.0) ++events[s];      // this column left its grid here
             }
-            S[s] = nv;
+            S[s] = nv[s];
         }
-        __syncthreads();
         pos += cut + 1;
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
             if (!((degraded >> s) & 1u) && events[s] > max_events) {
                 double part = 0.0;
-                for (int i = pos + tid; i < nt; i += GT) part += col[s][i];
-                S[s] = S[s] + block_sum_d(part, sh);
+                for (int i = pos + c.gtid; i < nt; i += c.gth) part += col[s][i];
+                S[s] = S[s] + c_reduce_d<false>(c, part);
                 degraded |= 1u << s;
             }
         }
@@ -553,22 +711,29 @@ __device__ void faithful_init_sums(const double* const (&col)[NC], int nt, doubl
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// the greedy kernel
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
                                                         int64_t* counts, double* state, ParWork w) {
     __shared__ Sh sh;
-    __shared__ int cnt_sh[QA_NFMT];
+    Coop c(sh);
     const int tid = threadIdx.x;
     const int base = ord.fmt[0];
     const bool is_pcc = metric == QA_METRIC_PCC;
-    for (int t = tid; t < nt; t += GT) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
-    if (tid < QA_NFMT) cnt_sh[tid] = tid == base ? nt : 0;
-    __syncthreads();
-
+    const int s_lo = is_pcc ? 0 : 3;
+    for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
+    if (tid < QA_NFMT) sh.cnt[tid] = 0;
+    if (c.gtid < QA_NFMT) counts[c.gtid] = c.gtid == base ? nt : 0;
+    Pcg g;
+    g.load(rng);
+    c.sync();
     const long long t_start = clock64();
+
     // ---- (1) initial sums, sequentially rounded in tile order ------------------------------
-    Consts c;
-    c.n = numel; c.thr = thr; c.metric = metric; c.sx = 0.0; c.sx2 = 0.0;
+    Consts k;
+    k.n = numel; k.thr = thr; k.metric = metric; k.sx = 0.0; k.sx2 = 0.0;
     double S[4] = {0.0, 0.0, 0.0, 0.0};      // sy, sy2, sxy, sabs
     unsigned degraded = 0;
     if (is_pcc) {
@@ -577,194 +742,189 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                                            table + (size_t)QA_STAT_FMT(base, 2) * nt, table + (size_t)QA_STAT_FMT(base, 3) * nt};
             double R[4];
             unsigned dg;
-            faithful_init_sums<4>(cols, nt, R, dg, 1 << 30, sh);
-            c.sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
+            faithful_init_sums<4>(c, cols, nt, R, dg, 1 << 30);
+            k.sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
         }
         {   // signed sums (means): faithful unless they keep hopping between binades
             const double* const cols[2] = {table + (size_t)QA_STAT_SX * nt, table + (size_t)QA_STAT_FMT(base, 0) * nt};
             double R[2];
-            faithful_init_sums<2>(cols, nt, R, degraded, 24, sh);
-            c.sx = R[0]; S[0] = R[1];
+            faithful_init_sums<2>(c, cols, nt, R, degraded, 24);
+            k.sx = R[0]; S[0] = R[1];
         }
     } else {
         const double* const cols[1] = {table + (size_t)QA_STAT_FMT(base, 3) * nt};
         double R[1];
         unsigned dg;
-        faithful_init_sums<1>(cols, nt, R, dg, 1 << 30, sh);
+        faithful_init_sums<1>(c, cols, nt, R, dg, 1 << 30);
         S[3] = R[0];
     }
-    Pcg g;
-    g.load(rng);
+    consts_finish(k);
     unsigned chain_rounds = 0;
-    long long t_mark = clock64(), cyc_init = 0, cyc_perm = 0, cyc_chain = 0;
-    cyc_init = t_mark - t_start;
+    long long t_mark = clock64(), cyc_perm = 0, cyc_chain = 0;
+    const long long cyc_init = t_mark - t_start;
+    const int CHc = c.gth * EPT;
 
     for (int fi = 0; fi < ord.n; ++fi) {
         const int fmt = ord.fmt[fi];
         // ---- candidates = not-fixed tiles in ascending order ------------------------------
         int m;
         {
-            const int per = (nt + GT - 1) / GT;
-            const int b = min(nt, tid * per), e = min(nt, b + per);
+            const int per = (nt + c.gth - 1) / c.gth;
+            const int b = min(nt, c.gtid * per), e = min(nt, b + per);
             int local = 0;
             for (int t = b; t < e; ++t) local += w.fixed[t] ? 0 : 1;
-            int run = block_scan_excl(local, m, sh);
+            int run = c_scan_excl(c, local, m);
             for (int t = b; t < e; ++t)
                 if (!w.fixed[t]) w.cand[run++] = t;
         }
-        __syncthreads();
+        c.sync();
         if (m == 0) break;
-        const bool base_pass = (fmt == base) && (fi == 0);
+        const bool base_pass = fi == 0;
         // ---- (2) visiting order ----------------------------------------------------------
         t_mark = clock64();
-        permutation_par(g, m, w.cand, w.order, w, !base_pass, sh);
+        permutation_par(c, g, m, w.cand, w.order, w, !base_pass);
         cyc_perm += clock64() - t_mark;
         t_mark = clock64();
         if (base_pass) {
-            // every candidate already has this format: the state cannot change, so all of them
-            // see the same test (mixed_tile_greedy.py:238-241)
-            if (!good_par(c, S)) {
-                for (int k = tid; k < m; k += GT) w.fixed[w.cand[k]] = 1;
+            // every candidate already has this format: the state cannot change, so all of them see the
+            // same test (mixed_tile_greedy.py:238-241)
+            if (!good_par(k, S)) {
+                for (int q = c.gtid; q < m; q += c.gth) w.fixed[w.cand[q]] = 1;
             }
-            __syncthreads();
+            c.sync();
             continue;
         }
-        const double* fcol[4] = {table + (size_t)QA_STAT_FMT(fmt, 0) * nt, table + (size_t)QA_STAT_FMT(fmt, 1) * nt,
-                                 table + (size_t)QA_STAT_FMT(fmt, 2) * nt, table + (size_t)QA_STAT_FMT(fmt, 3) * nt};
-        const int s_lo = is_pcc ? 0 : 3;
+        // every candidate of pass fi was accepted in pass fi-1 (rejected tiles are fixed), so its
+        // current format is the previous one in the order
+        const int prev = ord.fmt[fi - 1];
+        double* dq[4] = {w.dbuf, w.dbuf + (size_t)nt, w.dbuf + 2 * (size_t)nt, w.dbuf + 3 * (size_t)nt};
+        for (int q = c.gtid; q < m; q += c.gth) {      // gather the deltas once, in visiting order
+            const int t = w.order[q];
+            for (int s = s_lo; s < 4; ++s)
+                dq[s][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, s) * nt + t], table[(size_t)QA_STAT_FMT(prev, s) * nt + t]);
+        }
+        c.sync();
         // ---- (3) accept / reject chain -------------------------------------------------------
         int pos = 0;
         bool guess = true;                      // initial guess for a chunk: accept everything
         while (pos < m) {
-            const int len = min(CH, m - pos);
-            int tile[EPT], prev[EPT];
+            const int len = min(CHc, m - pos);
             double d[4][EPT];
             P2 cls[4][EPT], ex[4][EPT];
-            bool F[EPT], D[EPT], same[EPT];
+            bool F[EPT], D[EPT];
             Grid gr[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) gr[s] = make_grid(S[s]);
             int bad = len;
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int idx = tid * EPT + k;
-                tile[k] = -1; prev[k] = 0; same[k] = false; F[k] = false; D[k] = false;
+            for (int e = 0; e < EPT; ++e) {
+                const int idx = c.gtid * EPT + e;
+                F[e] = false; D[e] = false;
 #pragma unroll
-                for (int s = 0; s < 4; ++s) { d[s][k] = 0.0; cls[s][k] = P2{0, 0}; ex[s][k] = P2{0, 0}; }
+                for (int s = 0; s < 4; ++s) { d[s][e] = 0.0; cls[s][e] = P2{0, 0}; ex[s][e] = P2{0, 0}; }
                 if (idx < len) {
-                    const int t = w.order[pos + idx];
-                    tile[k] = t;
-                    prev[k] = assignment[t];
-                    same[k] = prev[k] == fmt;
-                    if (!same[k]) {
-                        F[k] = guess;
-                        for (int s = s_lo; s < 4; ++s) {
-                            d[s][k] = __dsub_rn(fcol[s][t], table[(size_t)QA_STAT_FMT(prev[k], s) * nt + t]);
-                            if (!classify(gr[s], d[s][k], cls[s][k])) bad = min(bad, idx);
-                        }
+                    F[e] = guess;
+                    for (int s = s_lo; s < 4; ++s) {
+                        d[s][e] = dq[s][pos + idx];
+                        if (!classify(gr[s], d[s][e], cls[s][e])) bad = min(bad, idx);
                     }
                 }
             }
-            bad = block_min(bad, sh);            // the element at `bad` is added for real and ends the chunk
+            bad = c_min(c, bad);                 // the element at `bad` is added for real and ends the chunk
             int valid = min(len, bad + 1);
             for (int round = 0; round < 64; ++round) {
                 ++chain_rounds;
                 unsigned on = 0;
 #pragma unroll
-                for (int k = 0; k < EPT; ++k)
-                    if (F[k] && (tid * EPT + k) < valid && (tid * EPT + k) != bad) on |= 1u << k;
-                scan_p2<4>(cls, on, ex, sh);
+                for (int e = 0; e < EPT; ++e)
+                    if (F[e] && (c.gtid * EPT + e) < valid && (c.gtid * EPT + e) != bad) on |= 1u << e;
+                scan_p2<4>(c, cls, on, ex);
                 int cut = valid - 1;             // last element that may be committed this round
                 int mism = 1 << 30;
 #pragma unroll
-                for (int k = 0; k < EPT; ++k) {
-                    const int idx = tid * EPT + k;
-                    D[k] = false;
+                for (int e = 0; e < EPT; ++e) {
+                    const int idx = c.gtid * EPT + e;
+                    D[e] = false;
                     if (idx < valid) {
                         double cnd[4];
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
-                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], ex[s][k])) : S[s];
-                            cnd[s] = same[k] ? sb : __dadd_rn(sb, d[s][k]);
+                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], ex[s][e])) : S[s];
+                            cnd[s] = __dadd_rn(sb, d[s][e]);
                         }
-                        D[k] = good_par(c, cnd);
-                        if (!same[k]) {
-                            if (D[k] != F[k]) mism = min(mism, idx);
-                            if ((on >> k) & 1u) {
-                                // an accepted element must leave every running sum inside its binade
-                                for (int s = s_lo; s < 4; ++s) {
-                                    const long long mi = m_after(gr[s], p2_then(ex[s][k], cls[s][k]));
-                                    if (gr[s].q != 0.0 && (mi < M_LO || mi >= M_HI)) cut = min(cut, idx);
-                                }
-                            }
+                        D[e] = good_par(k, cnd);
+                        if (D[e] != F[e]) mism = min(mism, idx);
+                        if ((on >> e) & 1u) {
+                            // an accepted element must leave every running sum inside its binade
+                            for (int s = s_lo; s < 4; ++s)
+                                if (gr[s].q != 0.0 && !in_binade(m_after(gr[s], p2_then(ex[s][e], cls[s][e])))) cut = min(cut, idx);
                         }
                     }
                 }
-                mism = block_min(mism, sh);
-                cut = block_min(cut, sh);
+                mism = c_min(c, mism);
+                cut = c_min(c, cut);
                 if (mism > cut) { valid = cut + 1; break; }       // flags are consistent up to the cut
-                if (round == 63) { valid = mism + 1; }            // pathological: commit up to the first wrong flag
+                if (round == 63) valid = mism + 1;                // pathological: commit up to the first wrong flag
                 // fix the first wrong flag; later ones take the freshly computed decisions as the new guess
 #pragma unroll
-                for (int k = 0; k < EPT; ++k) {
-                    const int idx = tid * EPT + k;
-                    if (idx >= mism && idx < valid && !same[k]) F[k] = D[k];
+                for (int e = 0; e < EPT; ++e) {
+                    const int idx = c.gtid * EPT + e;
+                    if (idx >= mism && idx < valid) F[e] = D[e];
                 }
             }
             // ---- commit [0, valid): D holds the decisions, ex the exact states before each element ----
-            int loc[QA_NFMT] = {0, 0, 0, 0};
+            int loc = 0;
+            bool owner = false;
+            double vals[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int idx = tid * EPT + k;
+            for (int e = 0; e < EPT; ++e) {
+                const int idx = c.gtid * EPT + e;
                 if (idx < valid) {
-                    const bool take = !same[k] && D[k];
-                    if (same[k]) { if (!D[k]) w.fixed[tile[k]] = 1; }
-                    else if (take) {
-                        assignment[tile[k]] = (int8_t)fmt;
-#pragma unroll
-                        for (int f = 0; f < QA_NFMT; ++f) loc[f] += (f == fmt) - (f == prev[k]);
-                    } else w.fixed[tile[k]] = 1;
+                    const int t = w.order[pos + idx];
+                    if (D[e]) { assignment[t] = (int8_t)fmt; ++loc; }
+                    else w.fixed[t] = 1;
                     if (idx == valid - 1) {
+                        owner = true;
 #pragma unroll
                         for (int s = 0; s < 4; ++s) {
-                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], ex[s][k])) : S[s];
-                            sh.f64[s] = take ? __dadd_rn(sb, d[s][k]) : sb;
+                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], ex[s][e])) : S[s];
+                            vals[s] = D[e] ? __dadd_rn(sb, d[s][e]) : sb;
                         }
-                        sh.flag = take ? 1 : 0;
+                        vals[4] = D[e] ? 1.0 : 0.0;
                     }
                 }
             }
+            loc = __reduce_add_sync(0xFFFFFFFFu, loc);
+            if ((tid & 31) == 0 && loc) { atomicAdd(&sh.cnt[fmt], loc); atomicAdd(&sh.cnt[prev], -loc); }
+            double nv[5];
+            c_bcast_d(c, owner, vals, 5, nv);
 #pragma unroll
-            for (int f = 0; f < QA_NFMT; ++f) {
-                const int v = __reduce_add_sync(0xFFFFFFFFu, loc[f]);
-                if ((tid & 31) == 0 && v) atomicAdd(&cnt_sh[f], v);
-            }
-            __syncthreads();
-#pragma unroll
-            for (int s = 0; s < 4; ++s) S[s] = sh.f64[s];
-            guess = sh.flag != 0;
+            for (int s = 0; s < 4; ++s) S[s] = nv[s];
+            guess = nv[4] != 0.0;
             pos += valid;
-            __syncthreads();
         }
         cyc_chain += clock64() - t_mark;
     }
-    if (tid == 0) {
+    // max |x - y| of the final assignment (for the reported atol)
+    c.sync();
+    double amax = 0.0;
+    for (int t = c.gtid; t < nt; t += c.gth) amax = fmax(amax, table[(size_t)QA_STAT_FMT(assignment[t], 4) * nt + t]);
+    amax = c_reduce_d<true>(c, amax);
+    __syncthreads();
+    if (tid < QA_NFMT && sh.cnt[tid] != 0)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&counts[tid]), (unsigned long long)(long long)sh.cnt[tid]);
+    if (c.gtid == 0) {
         g.store(rng);
-        for (int f = 0; f < QA_NFMT; ++f) counts[f] = cnt_sh[f];
-        state[0] = c.sx; state[1] = c.sx2; state[2] = S[0]; state[3] = S[1]; state[4] = S[2]; state[5] = S[3];
+        state[0] = k.sx; state[1] = k.sx2; state[2] = S[0]; state[3] = S[1]; state[4] = S[2]; state[5] = S[3];
         state[6] = (double)degraded + 65536.0 * (double)chain_rounds;
-        state[7] = is_pcc ? pcc_value_par(c, S[0], S[1], S[2], S[3]) : (numel != 0.0 ? __ddiv_rn(S[3], numel) : 0.0);
+        state[7] = is_pcc ? pcc_value_par(k, S[0], S[1], S[2], S[3]) : (numel != 0.0 ? __ddiv_rn(S[3], numel) : 0.0);
         state[8] = (double)cyc_init; state[9] = (double)cyc_perm; state[10] = (double)cyc_chain;   // SM cycles per phase
+        state[11] = amax;
+        state[12] = (double)c.nr;
     }
 }
 
 static inline int64_t al(int64_t v) { return (v + 255) / 256 * 256; }
-
-}  // namespace qa
-
-using namespace qa;
-
-extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(n) + 512; }
 
 static ParWork carve(void* work, int64_t n) {
     ParWork w;
@@ -778,15 +938,56 @@ static ParWork carve(void* work, int64_t n) {
     w.bucket = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.succ = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.parent = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
+    w.dbuf = reinterpret_cast<double*>(take(32 * n));
     w.fixed = reinterpret_cast<uint8_t*>(take(n));
     return w;
 }
 
+static int pick_cluster(int64_t n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("QA_GREEDY_CLUSTER");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) return forced > MAXR ? MAXR : forced;
+    int r = 1;
+    while (r < 8 && (int64_t)r * GT * EPT * 2 < n) r <<= 1;     // grow until ~2 chunks cover the tensor, at most 8 CTAs
+    return r;
+}
+
+template <typename... KArgs, typename... Args>
+static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
+    if (nr > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nr, 1, 1);
+    cfg.blockDim = dim3(GT, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = nr;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess) {
+        set_error("cluster launch (%d CTAs): %s", nr, cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}
+
+}  // namespace qa
+
+using namespace qa;
+
+extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(32 * n) + al(n) + 512; }
+
 extern "C" int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* work, qa_stream_t stream) {
     if (!rng || n < 0 || n > 0x3FFFFFFF || (n > 0 && (!out_perm || !work))) { set_error("qa_numpy_permutation_par: bad args"); return 1; }
     if (n == 0) return 0;
-    permutation_par_kernel<<<1, GT, 0, (cudaStream_t)stream>>>(rng, (int)n, out_perm, carve(work, n));
-    return check_launch("qa_numpy_permutation_par");
+    return launch_cluster(permutation_par_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, out_perm, carve(work, n));
 }
 
 extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric, double threshold,
@@ -803,7 +1004,6 @@ extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double 
     for (int i = 0; i < QA_NFMT; ++i) ord.fmt[i] = i < nfmt ? fmt_order[i] : 0;
     for (int i = 0; i < nfmt; ++i)
         if (ord.fmt[i] < 0 || ord.fmt[i] >= QA_NFMT) { set_error("qa_greedy_assign_par: bad format index"); return 1; }
-    greedy_par_kernel<<<1, GT, 0, (cudaStream_t)stream>>>(table, (int)ntiles, numel, metric, threshold, ord, rng, assignment,
-                                                          counts, state, carve(work, ntiles));
-    return check_launch("qa_greedy_assign_par");
+    return launch_cluster(greedy_par_kernel, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel, metric,
+                          threshold, ord, rng, assignment, counts, state, carve(work, ntiles));
 }
