@@ -96,7 +96,7 @@ int qa_numpy_integers(qa_pcg64* rng, int k, int64_t n, int8_t* out_vals, qa_stre
  * Replaces MixedTileGreedyCompression._compress, mixed_tile_greedy.py:135-346, driven by the
  * tile-stat table.  fmt_order[nfmt] = candidate formats (first = base).  numel = element count
  * of the original tensor.  Outputs: assignment int8[ntiles]; counts int64[QA_NFMT];
- * state double[16] = final {sx, sx2, sy, sy2, sxy, sabs, max_abs, value, diagnostics...}.
+ * state double[24] = final {sx, sx2, sy, sy2, sxy, sabs, max_abs, value, diagnostics...}.
  * work: at least qa_greedy_work_bytes(ntiles) bytes. */
 int64_t qa_greedy_work_bytes(int64_t ntiles);
 int qa_greedy_assign(const double* table, int64_t ntiles, double numel, int metric,

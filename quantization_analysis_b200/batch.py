@@ -35,7 +35,7 @@ class GreedyBatch:
                 "table": torch.zeros((NSTAT, nt), dtype=torch.float64, device=self.device),
                 "assignment": torch.empty(nt, dtype=torch.int8, device=self.device),
                 "counts": torch.zeros(NFMT, dtype=torch.int64, device=self.device),
-                "state": torch.zeros(16, dtype=torch.float64, device=self.device),
+                "state": torch.zeros(24, dtype=torch.float64, device=self.device),
                 "sums": torch.zeros(8, dtype=torch.float64, device=self.device),
                 "work": torch.empty(max(L.qa_greedy_work_bytes(nt), L.qa_greedy_par_work_bytes(nt)), dtype=torch.uint8,
                                     device=self.device),

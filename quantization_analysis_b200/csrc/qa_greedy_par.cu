@@ -38,7 +38,7 @@ constexpr int GT = 512;           // threads per CTA
 constexpr int NW = GT / 32;
 constexpr int MAXR = 16;          // largest cluster
 constexpr int DPT = 8;            // draws per thread per round (4 LCG outputs)
-constexpr int EPT = 2;            // chain elements per thread per chunk
+constexpr int EPS = 4;           // elements each thread streams through per chunk (scan works on thread totals)
 constexpr int SEQ_TAIL = 96;      // last Fisher-Yates steps are drawn by one thread
 constexpr long long M_LO = 1ll << 52, M_HI = 1ll << 53;
 
@@ -65,7 +65,7 @@ struct P2 {          // increment of m if the incoming m is even / odd
 };
 
 struct Sh {
-    int i32[40];
+    int i32[2 * NW + 8];
     long long i64[NW * 6 * 2 + 16];
     double f64[16];
     // cluster exchange (double buffered; written by remote CTAs through DSMEM)
@@ -255,22 +255,15 @@ __device__ __forceinline__ P2 shfl_up_p2(P2 v, int o) {
     return y;
 }
 
-// Exclusive cluster-wide scan of NS P2 streams, EPT elements per thread (element order = cluster
-// thread-major); element k of a thread takes part iff bit k of `on` is set.
+// Exclusive cluster-wide scan (cluster thread order) of one P2 per stream per thread.
 template <int NS>
-__device__ __forceinline__ void scan_p2(Coop& c, const P2 (&cls)[NS][EPT], unsigned on, P2 (&ex)[NS][EPT]) {
+__device__ __forceinline__ void scan_totals(Coop& c, const P2 (&tot)[NS], P2 (&pre)[NS]) {
     Sh& sh = c.sh;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     P2 inc[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        P2 run{0, 0};
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-            ex[s][k] = run;
-            if ((on >> k) & 1u) run = p2_then(run, cls[s][k]);
-        }
-        inc[s] = run;
+        inc[s] = tot[s];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const P2 y = shfl_up_p2(inc[s], o);
@@ -299,7 +292,6 @@ __device__ __forceinline__ void scan_p2(Coop& c, const P2 (&cls)[NS][EPT], unsig
         }
     }
     __syncthreads();
-    P2 pre[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         pre[s].d0 = sh.i64[(w * NS + s) * 2];
@@ -325,10 +317,32 @@ __device__ __forceinline__ void scan_p2(Coop& c, const P2 (&cls)[NS][EPT], unsig
     } else {
         __syncthreads();
     }
+}
+
+// three cluster-wide minima in one exchange
+__device__ __forceinline__ void c_min3(Coop& c, int& v0, int& v1, int& v2) {
+    v0 = __reduce_min_sync(0xFFFFFFFFu, v0);
+    v1 = __reduce_min_sync(0xFFFFFFFFu, v1);
+    v2 = __reduce_min_sync(0xFFFFFFFFu, v2);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { c.sh.i32[w] = v0; c.sh.i32[NW + w] = v1; c.sh.i64[w] = v2; }
+    __syncthreads();
+    int r0 = c.sh.i32[0], r1 = c.sh.i32[NW], r2 = (int)c.sh.i64[0];
 #pragma unroll
-    for (int s = 0; s < NS; ++s)
-#pragma unroll
-        for (int k = 0; k < EPT; ++k) ex[s][k] = p2_then(pre[s], ex[s][k]);
+    for (int i = 1; i < NW; ++i) { r0 = min(r0, c.sh.i32[i]); r1 = min(r1, c.sh.i32[NW + i]); r2 = min(r2, (int)c.sh.i64[i]); }
+    __syncthreads();
+    if (c.nr > 1) {
+        const unsigned b = c.par++ & 1u;
+        if (threadIdx.x < c.nr) {
+            long long* dst = c.cl.map_shared_rank(&c.sh.xl[b][c.rank][0], threadIdx.x);
+            dst[0] = r0; dst[1] = r1; dst[2] = r2;
+        }
+        c.cl.sync();
+        for (unsigned q = 0; q < c.nr; ++q) {
+            r0 = min(r0, (int)c.sh.xl[b][q][0]); r1 = min(r1, (int)c.sh.xl[b][q][1]); r2 = min(r2, (int)c.sh.xl[b][q][2]);
+        }
+    }
+    v0 = r0; v1 = r1; v2 = r2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,14 +533,14 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
         }
         c.sh.i64[0] = (long long)t.s.hi;
         c.sh.i64[1] = (long long)t.s.lo;
-        c.sh.i32[34] = (int)t.has32;
-        c.sh.i32[35] = (int)t.buf32;
+        c.sh.i32[2 * NW + 2] = (int)t.has32;
+        c.sh.i32[2 * NW + 3] = (int)t.buf32;
     }
     __syncthreads();
     g.s.hi = (uint64_t)c.sh.i64[0];
     g.s.lo = (uint64_t)c.sh.i64[1];
-    g.has32 = (uint32_t)c.sh.i32[34];
-    g.buf32 = (uint32_t)c.sh.i32[35];
+    g.has32 = (uint32_t)c.sh.i32[2 * NW + 2];
+    g.buf32 = (uint32_t)c.sh.i32[2 * NW + 3];
     c.sync();
     if (!apply) return;
 
@@ -610,76 +624,100 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
     Sh& sh = c.sh;
     const int tid = threadIdx.x;
     constexpr int HEAD = 192;
+    static_assert(HEAD <= GT, "head is staged by one CTA pass");
     int events[NC];
 #pragma unroll
     for (int s = 0; s < NC; ++s) { S[s] = 0.0; events[s] = 0; }
     degraded = 0;
     int pos = min(nt, HEAD);
-    if (tid < NC) {
-        double acc = 0.0;
-        const double* cp = col[0];
+    {   // stage the head in shared memory (parallel loads), then one thread adds each column up in order
+        double* stage = reinterpret_cast<double*>(sh.i64);
+        static_assert(sizeof(sh.i64) >= sizeof(double) * HEAD, "head staging does not fit");
 #pragma unroll
-        for (int s = 0; s < NC; ++s) if (s == tid) cp = col[s];
-        for (int i = 0; i < pos; ++i) acc = __dadd_rn(acc, cp[i]);
-        sh.f64[tid] = acc;
+        for (int s = 0; s < NC; ++s) {
+            __syncthreads();
+            if (tid < pos) stage[tid] = col[s][tid];
+            __syncthreads();
+            if (tid == 0) {
+                double acc = 0.0;
+                for (int i = 0; i < pos; ++i) acc = __dadd_rn(acc, stage[i]);
+                sh.f64[s] = acc;
+            }
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < NC; ++s) S[s] = sh.f64[s];
     __syncthreads();
-    const int CHc = c.gth * EPT;
+    const int CHc = c.gth * EPS;
     while (pos < nt) {
         const int len = min(CHc, nt - pos);
+        const int lo = c.gtid * EPS, hi = min(len, lo + EPS);          // this thread streams elements [lo, hi)
         Grid g[NC];
-        P2 cls[NC][EPT], ex[NC][EPT];
-        double t[NC][EPT];
-        int bad = len;                                  // first element that cannot ride the grid
 #pragma unroll
-        for (int s = 0; s < NC; ++s) {
-            g[s] = make_grid(S[s]);
+        for (int s = 0; s < NC; ++s) g[s] = make_grid(S[s]);
+        // walk 1: compose this thread's additions (stop at the first one that cannot ride the grid)
+        P2 tot[NC], pre0[NC];
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                const int idx = c.gtid * EPT + k;
-                t[s][k] = idx < len ? col[s][pos + idx] : 0.0;
-                cls[s][k] = P2{0, 0};
-                if (idx < len && !((degraded >> s) & 1u)) {
-                    if (!classify(g[s], t[s][k], cls[s][k])) bad = min(bad, idx);
+        for (int s = 0; s < NC; ++s) tot[s] = P2{0, 0};
+        int bad = 0x7FFFFFFF;
+        for (int idx = lo; idx < hi && bad == 0x7FFFFFFF; ++idx) {
+            P2 p[NC];
+            bool ok = true;
+#pragma unroll
+            for (int s = 0; s < NC; ++s) {
+                p[s] = P2{0, 0};
+                if (!((degraded >> s) & 1u)) ok = classify(g[s], col[s][pos + idx], p[s]) && ok;
+            }
+            if (!ok) { bad = idx; break; }
+#pragma unroll
+            for (int s = 0; s < NC; ++s) tot[s] = p2_then(tot[s], p[s]);
+        }
+        scan_totals<NC>(c, tot, pre0);
+        // walk 2: first element whose result leaves a binade (its own add is still exact)
+        int cut = len - 1, unused = 0x7FFFFFFF;
+        {
+            P2 run[NC];
+#pragma unroll
+            for (int s = 0; s < NC; ++s) run[s] = pre0[s];
+            for (int idx = lo; idx < hi && idx < bad; ++idx) {
+#pragma unroll
+                for (int s = 0; s < NC; ++s) {
+                    if ((degraded >> s) & 1u) continue;
+                    P2 p{0, 0};
+                    classify(g[s], col[s][pos + idx], p);
+                    run[s] = p2_then(run[s], p);
+                    if (g[s].q != 0.0 && !in_binade(m_after(g[s], run[s]))) cut = min(cut, idx);
                 }
+                if (cut == idx) break;
             }
         }
-        bad = c_min(c, bad);
-        unsigned on = 0;                                // elements before `bad` ride the scan
-#pragma unroll
-        for (int k = 0; k < EPT; ++k)
-            if (c.gtid * EPT + k < bad && c.gtid * EPT + k < len) on |= 1u << k;
-        scan_p2<NC>(c, cls, on, ex);
-        int cut = min(bad, len - 1);                    // last element handled this round
-#pragma unroll
-        for (int s = 0; s < NC; ++s) {
-            if ((degraded >> s) & 1u) continue;
-#pragma unroll
-            for (int k = 0; k < EPT; ++k) {
-                if (((on >> k) & 1u) && g[s].q != 0.0 && !in_binade(m_after(g[s], p2_then(ex[s][k], cls[s][k]))))
-                    cut = min(cut, c.gtid * EPT + k);
-            }
-        }
-        cut = c_min(c, cut);
+        c_min3(c, bad, cut, unused);
+        cut = min(cut, bad);
         // state after element `cut` = fl(S_before(cut) + t_cut): a real add from the exact state before it
         double nv[NC];
         {
-            const bool owner = cut / EPT == c.gtid;
+            const bool owner = cut >= lo && cut < lo + EPS;
             double vals[NC];
 #pragma unroll
             for (int s = 0; s < NC; ++s) vals[s] = 0.0;
             if (owner) {
+                P2 run[NC];
 #pragma unroll
-                for (int k = 0; k < EPT; ++k) {
-                    if (k != cut % EPT) continue;
+                for (int s = 0; s < NC; ++s) run[s] = pre0[s];
+                for (int idx = lo; idx < cut; ++idx) {
 #pragma unroll
                     for (int s = 0; s < NC; ++s) {
-                        const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], ex[s][k])) : S[s];
-                        vals[s] = __dadd_rn(before, t[s][k]);
+                        if ((degraded >> s) & 1u) continue;
+                        P2 p{0, 0};
+                        classify(g[s], col[s][pos + idx], p);
+                        run[s] = p2_then(run[s], p);
                     }
+                }
+#pragma unroll
+                for (int s = 0; s < NC; ++s) {
+                    const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], run[s])) : S[s];
+                    vals[s] = __dadd_rn(before, col[s][pos + cut]);
                 }
             }
             c_bcast_d(c, owner, vals, NC, nv);
@@ -714,6 +752,7 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
 // ---------------------------------------------------------------------------------------------
 // the greedy kernel
 // ---------------------------------------------------------------------------------------------
+template <bool PCC>
 __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
                                                         int64_t* counts, double* state, ParWork w) {
@@ -721,8 +760,9 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     Coop c(sh);
     const int tid = threadIdx.x;
     const int base = ord.fmt[0];
-    const bool is_pcc = metric == QA_METRIC_PCC;
-    const int s_lo = is_pcc ? 0 : 3;
+    constexpr bool is_pcc = PCC;
+    constexpr int NS = PCC ? 4 : 1;       // running sums that drive the decision: sy, sy2, sxy, sabs | sabs
+    constexpr int S0 = PCC ? 0 : 3;       // first table statistic among them
     for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
     if (tid < QA_NFMT) sh.cnt[tid] = 0;
     if (c.gtid < QA_NFMT) counts[c.gtid] = c.gtid == base ? nt : 0;
@@ -734,7 +774,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     // ---- (1) initial sums, sequentially rounded in tile order ------------------------------
     Consts k;
     k.n = numel; k.thr = thr; k.metric = metric; k.sx = 0.0; k.sx2 = 0.0;
-    double S[4] = {0.0, 0.0, 0.0, 0.0};      // sy, sy2, sxy, sabs
+    double S[4] = {0.0, 0.0, 0.0, 0.0};      // sy, sy2, sxy, sabs (mae uses S[3] only)
     unsigned degraded = 0;
     if (is_pcc) {
         {   // sums of non-negative terms: few binade changes, always carried faithfully
@@ -761,8 +801,9 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     consts_finish(k);
     unsigned chain_rounds = 0;
     long long t_mark = clock64(), cyc_perm = 0, cyc_chain = 0;
+    long long cy_load = 0, cy_scan = 0, cy_dec = 0, cy_min = 0, cy_commit = 0, cy_gather = 0, tq = 0;
     const long long cyc_init = t_mark - t_start;
-    const int CHc = c.gth * EPT;
+    const int CHc = c.gth * EPS;
 
     for (int fi = 0; fi < ord.n; ++fi) {
         const int fmt = ord.fmt[fi];
@@ -798,110 +839,140 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         // current format is the previous one in the order
         const int prev = ord.fmt[fi - 1];
         double* dq[4] = {w.dbuf, w.dbuf + (size_t)nt, w.dbuf + 2 * (size_t)nt, w.dbuf + 3 * (size_t)nt};
+        tq = clock64();
         for (int q = c.gtid; q < m; q += c.gth) {      // gather the deltas once, in visiting order
             const int t = w.order[q];
-            for (int s = s_lo; s < 4; ++s)
-                dq[s][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, s) * nt + t], table[(size_t)QA_STAT_FMT(prev, s) * nt + t]);
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                dq[s][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, S0 + s) * nt + t], table[(size_t)QA_STAT_FMT(prev, S0 + s) * nt + t]);
         }
         c.sync();
+        cy_gather += clock64() - tq;
         // ---- (3) accept / reject chain -------------------------------------------------------
         int pos = 0;
         bool guess = true;                      // initial guess for a chunk: accept everything
         while (pos < m) {
             const int len = min(CHc, m - pos);
-            double d[4][EPT];
-            P2 cls[4][EPT], ex[4][EPT];
-            bool F[EPT], D[EPT];
-            Grid gr[4];
+            const int lo = c.gtid * EPS, hi = min(len, lo + EPS);      // this thread streams elements [lo, hi)
+            const int cnt = max(0, hi - lo);
+            tq = clock64();
+            Grid gr[NS];
 #pragma unroll
-            for (int s = 0; s < 4; ++s) gr[s] = make_grid(S[s]);
-            int bad = len;
-#pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int idx = c.gtid * EPT + e;
-                F[e] = false; D[e] = false;
-#pragma unroll
-                for (int s = 0; s < 4; ++s) { d[s][e] = 0.0; cls[s][e] = P2{0, 0}; ex[s][e] = P2{0, 0}; }
-                if (idx < len) {
-                    F[e] = guess;
-                    for (int s = s_lo; s < 4; ++s) {
-                        d[s][e] = dq[s][pos + idx];
-                        if (!classify(gr[s], d[s][e], cls[s][e])) bad = min(bad, idx);
-                    }
-                }
-            }
-            bad = c_min(c, bad);                 // the element at `bad` is added for real and ends the chunk
-            int valid = min(len, bad + 1);
+            for (int s = 0; s < NS; ++s) gr[s] = make_grid(S[S0 + s]);
+            unsigned F = guess && cnt > 0 ? (0xFFFFFFFFu >> (32 - cnt)) : 0u;     // accept flags, bit j <-> element lo + j
+            unsigned D = 0;
+            int valid = len;
+            P2 pre0[NS];
+            cy_load += clock64() - tq;
             for (int round = 0; round < 64; ++round) {
                 ++chain_rounds;
-                unsigned on = 0;
+                tq = clock64();
+                // walk 1: compose the accepted elements of this thread
+                P2 tot[NS];
 #pragma unroll
-                for (int e = 0; e < EPT; ++e)
-                    if (F[e] && (c.gtid * EPT + e) < valid && (c.gtid * EPT + e) != bad) on |= 1u << e;
-                scan_p2<4>(c, cls, on, ex);
-                int cut = valid - 1;             // last element that may be committed this round
-                int mism = 1 << 30;
+                for (int s = 0; s < NS; ++s) tot[s] = P2{0, 0};
+                int bad = 0x7FFFFFFF;           // first accepted element that cannot ride the grid
+                for (int j = 0; j < cnt && lo + j < valid; ++j) {
+                    if (!((F >> j) & 1u)) continue;
+                    P2 p[NS];
+                    bool ok = true;
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const int idx = c.gtid * EPT + e;
-                    D[e] = false;
-                    if (idx < valid) {
-                        double cnd[4];
+                    for (int s = 0; s < NS; ++s) ok = classify(gr[s], dq[s][pos + lo + j], p[s]) && ok;
+                    if (!ok) { bad = lo + j; break; }
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], ex[s][e])) : S[s];
-                            cnd[s] = __dadd_rn(sb, d[s][e]);
+                    for (int s = 0; s < NS; ++s) tot[s] = p2_then(tot[s], p[s]);
+                }
+                scan_totals<NS>(c, tot, pre0);
+                cy_scan += clock64() - tq; tq = clock64();
+                // walk 2: exact state before every element -> decision; first wrong flag; first binade exit
+                int mism = 0x7FFFFFFF, cut = 0x7FFFFFFF;
+                D = 0;
+                {
+                    P2 run[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) run[s] = pre0[s];
+                    for (int j = 0; j < cnt && lo + j < valid; ++j) {
+                        const int idx = lo + j;
+                        double cnd[4] = {0.0, 0.0, 0.0, 0.0}, dl[NS];
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            dl[s] = dq[s][pos + idx];
+                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
+                            cnd[S0 + s] = __dadd_rn(sb, dl[s]);
                         }
-                        D[e] = good_par(k, cnd);
-                        if (D[e] != F[e]) mism = min(mism, idx);
-                        if ((on >> e) & 1u) {
-                            // an accepted element must leave every running sum inside its binade
-                            for (int s = s_lo; s < 4; ++s)
-                                if (gr[s].q != 0.0 && !in_binade(m_after(gr[s], p2_then(ex[s][e], cls[s][e])))) cut = min(cut, idx);
+                        const bool dj = good_par(k, cnd);
+                        const bool fj = (F >> j) & 1u;
+                        D |= dj ? (1u << j) : 0u;
+                        if (dj != fj) mism = min(mism, idx);
+                        if (fj) {
+                            if (idx == bad) { cut = min(cut, idx); break; }     // added for real; ends the chunk
+#pragma unroll
+                            for (int s = 0; s < NS; ++s) {
+                                P2 p{0, 0};
+                                classify(gr[s], dl[s], p);
+                                run[s] = p2_then(run[s], p);
+                                if (gr[s].q != 0.0 && !in_binade(m_after(gr[s], run[s]))) cut = min(cut, idx);
+                            }
+                            if (cut == idx) break;
                         }
                     }
                 }
-                mism = c_min(c, mism);
-                cut = c_min(c, cut);
+                cy_dec += clock64() - tq; tq = clock64();
+                int unused = 0x7FFFFFFF;
+                c_min3(c, mism, cut, unused);
+                cy_min += clock64() - tq;
+                cut = min(cut, valid - 1);
                 if (mism > cut) { valid = cut + 1; break; }       // flags are consistent up to the cut
-                if (round == 63) valid = mism + 1;                // pathological: commit up to the first wrong flag
+                if (round == 63) { valid = mism + 1; }            // pathological: commit up to the first wrong flag
                 // fix the first wrong flag; later ones take the freshly computed decisions as the new guess
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    const int idx = c.gtid * EPT + e;
-                    if (idx >= mism && idx < valid) F[e] = D[e];
+                for (int j = 0; j < cnt; ++j) {
+                    const int idx = lo + j;
+                    if (idx >= mism && idx < valid) F = (F & ~(1u << j)) | (D & (1u << j));
                 }
+                if (round == 63) break;
             }
-            // ---- commit [0, valid): D holds the decisions, ex the exact states before each element ----
+            // ---- commit [0, valid): D holds the decisions; pre0 the exact prefix of this thread ----
+            tq = clock64();
             int loc = 0;
             bool owner = false;
             double vals[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int j = 0; j < cnt && lo + j < valid; ++j) {
+                const int t = w.order[pos + lo + j];
+                if ((D >> j) & 1u) { assignment[t] = (int8_t)fmt; ++loc; }
+                else w.fixed[t] = 1;
+            }
+            if (valid - 1 >= lo && valid - 1 < lo + EPS) {       // owner of the last committed element
+                owner = true;
+                P2 run[NS];
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int idx = c.gtid * EPT + e;
-                if (idx < valid) {
-                    const int t = w.order[pos + idx];
-                    if (D[e]) { assignment[t] = (int8_t)fmt; ++loc; }
-                    else w.fixed[t] = 1;
-                    if (idx == valid - 1) {
-                        owner = true;
+                for (int s = 0; s < NS; ++s) run[s] = pre0[s];
+                const int jl = valid - 1 - lo;
+                for (int j = 0; j < jl; ++j) {
+                    if (!((D >> j) & 1u)) continue;
 #pragma unroll
-                        for (int s = 0; s < 4; ++s) {
-                            const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], ex[s][e])) : S[s];
-                            vals[s] = D[e] ? __dadd_rn(sb, d[s][e]) : sb;
-                        }
-                        vals[4] = D[e] ? 1.0 : 0.0;
+                    for (int s = 0; s < NS; ++s) {
+                        P2 p{0, 0};
+                        classify(gr[s], dq[s][pos + lo + j], p);
+                        run[s] = p2_then(run[s], p);
                     }
                 }
+                const bool take = (D >> jl) & 1u;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
+                    vals[S0 + s] = take ? __dadd_rn(sb, dq[s][pos + valid - 1]) : sb;
+                }
+                vals[4] = take ? 1.0 : 0.0;
             }
             loc = __reduce_add_sync(0xFFFFFFFFu, loc);
             if ((tid & 31) == 0 && loc) { atomicAdd(&sh.cnt[fmt], loc); atomicAdd(&sh.cnt[prev], -loc); }
             double nv[5];
             c_bcast_d(c, owner, vals, 5, nv);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) S[s] = nv[s];
+            for (int s = 0; s < NS; ++s) S[S0 + s] = nv[S0 + s];
             guess = nv[4] != 0.0;
             pos += valid;
+            cy_commit += clock64() - tq;
         }
         cyc_chain += clock64() - t_mark;
     }
@@ -921,6 +992,8 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[8] = (double)cyc_init; state[9] = (double)cyc_perm; state[10] = (double)cyc_chain;   // SM cycles per phase
         state[11] = amax;
         state[12] = (double)c.nr;
+        state[13] = (double)cy_load + 1e-9 * 0; state[14] = (double)cy_scan; state[15] = (double)cy_dec;
+        state[16] = (double)cy_min; state[17] = (double)cy_commit; state[18] = (double)cy_gather;
     }
 }
 
@@ -951,7 +1024,8 @@ static int pick_cluster(int64_t n) {
     }
     if (forced > 0) return forced > MAXR ? MAXR : forced;
     int r = 1;
-    while (r < 8 && (int64_t)r * GT * EPT * 2 < n) r <<= 1;     // grow until ~2 chunks cover the tensor, at most 8 CTAs
+    while (r < 8 && (int64_t)r * GT * DPT < n) r <<= 1;          // grow until one draw round covers the tensor
+    if (n >= 65536) r = 16;                                      // opt-in (non-portable) size for the largest tensors
     return r;
 }
 
@@ -971,6 +1045,10 @@ static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args..
     cfg.attrs = at;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess && nr > 8) {           // no GPC can host 16 co-resident CTAs right now: portable size
+        (void)cudaGetLastError();
+        return launch_cluster(kern, 8, s, args...);
+    }
     if (e != cudaSuccess) {
         set_error("cluster launch (%d CTAs): %s", nr, cudaGetErrorString(e));
         return 2;
@@ -1004,6 +1082,9 @@ extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double 
     for (int i = 0; i < QA_NFMT; ++i) ord.fmt[i] = i < nfmt ? fmt_order[i] : 0;
     for (int i = 0; i < nfmt; ++i)
         if (ord.fmt[i] < 0 || ord.fmt[i] >= QA_NFMT) { set_error("qa_greedy_assign_par: bad format index"); return 1; }
-    return launch_cluster(greedy_par_kernel, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel, metric,
-                          threshold, ord, rng, assignment, counts, state, carve(work, ntiles));
+    if (metric == QA_METRIC_PCC)
+        return launch_cluster(greedy_par_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
+                              metric, threshold, ord, rng, assignment, counts, state, carve(work, ntiles));
+    return launch_cluster(greedy_par_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
+                          metric, threshold, ord, rng, assignment, counts, state, carve(work, ntiles));
 }

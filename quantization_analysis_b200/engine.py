@@ -203,7 +203,7 @@ def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float
         parallel = metric in ("pcc", "mae")
     assignment = torch.empty(nt, dtype=torch.int8, device=dev)
     counts = torch.zeros(NFMT, dtype=torch.int64, device=dev)
-    state = torch.zeros(16, dtype=torch.float64, device=dev)
+    state = torch.zeros(24, dtype=torch.float64, device=dev)
     order = _lib.int32_array([FMT_INDEX[f] for f in fmt_order])
     if parallel:
         work = torch.empty(L.qa_greedy_par_work_bytes(nt), dtype=torch.uint8, device=dev)
