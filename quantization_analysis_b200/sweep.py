@@ -1,0 +1,47 @@
+"""Threshold sweep on the device (core of scripts/sweep_mixed_tile_threshold.py:623-790).
+
+Per tensor: one pass for the NumPy-faithful per-tile scores, one for the tile-stat table; then all
+thresholds are assigned in ONE launch (`qa_threshold_assign`, index into the ascending-bytes order with the
+last format forced, :145-155) and every distinct assignment is scored from the table.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine
+from .compression_algorithms.mixed_tile_threshold import formats_by_precision
+from .compression_algorithms.tile_utils import MIXED_TILE_FORMATS, mixed_tile_total_bytes
+
+_ROW = {"pcc": 0, "mae": 1, "atol": 2}
+
+
+def sweep_thresholds(scores_metric: torch.Tensor, tile_formats, metric: str, steps: int, lowest: float) -> np.ndarray:
+    """np.linspace(max score of the highest-precision format, lowest, steps) as float32 (sweep:659-670)."""
+    order = formats_by_precision(tile_formats)
+    top = float(scores_metric[engine.FMT_INDEX[order[-1]]].max().item())
+    return np.linspace(top, lowest, steps, dtype=np.float32)
+
+
+def sweep_tensor(x, tile_formats=MIXED_TILE_FORMATS, metric: str = "pcc", steps: int = 32, lowest: float = 0.9,
+                 thresholds=None):
+    """-> list of dict rows (threshold, counts, total_bytes, pcc, mae, atol) and the int8 maps [steps, ntiles]."""
+    p = engine.prepare_tiles(x)
+    scores = engine.tile_scores(p, tile_formats)[_ROW[metric]].contiguous()
+    table = engine.tile_stats(p, MIXED_TILE_FORMATS)
+    if thresholds is None:
+        thresholds = sweep_thresholds(scores, tile_formats, metric, steps, lowest)
+    order = formats_by_precision(tile_formats)
+    maps, counts = engine.threshold_assign(scores, order, metric == "pcc", thresholds)
+    counts = counts.cpu().numpy()
+    rows, prev, prev_row = [], None, None
+    for i, thr in enumerate(thresholds):
+        if prev is not None and torch.equal(maps[i], prev):       # unchanged assignment: reuse (sweep:736-742)
+            row = dict(prev_row, threshold=float(thr))
+        else:
+            m = engine.metrics_from_sums(engine.assignment_sums(table, maps[i]).cpu().numpy(), p.numel)
+            c = {f: int(counts[i, j]) for j, f in enumerate(MIXED_TILE_FORMATS)}
+            row = {"threshold": float(thr), "counts": c, "total_bytes": mixed_tile_total_bytes(c), **m}
+        rows.append(row)
+        prev, prev_row = maps[i], row
+    return rows, maps

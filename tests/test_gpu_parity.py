@@ -231,3 +231,58 @@ def test_empty_and_scalar_inputs(qa):
     assert r.meta["assignment"].shape == (1, 1) and r.tile_counts == {f: 0 for f in G.MIXED}
     s = np.array(0.3, dtype=np.float32)
     assert qf.quantize_weight_values(s, "bfp4").shape == ()
+
+
+def test_sweep_matches_oracle(qa):
+    """Threshold sweep (scripts/sweep_mixed_tile_threshold.py:145-155, 659-670): maps bit-equal for all
+    thresholds, whole-tensor metrics within 1e-6 of the fp64 formulas."""
+    from quantization_analysis_b200 import sweep
+    x = G.algo_input("het_256x512")
+    for metric, lowest in (("pcc", 0.9), ("mae", 5e-3), ("atol", 0.05)):
+        sc = orc.padded_tile_scores(x, G.MIXED, metric)
+        top = float(np.max(sc["bf16"]))
+        thr = np.linspace(top, lowest, 16, dtype=np.float32)
+        want = orc.sweep_assign(sc, G.MIXED, metric, thr)
+        rows, maps = sweep.sweep_tensor(x, G.MIXED, metric, steps=16, lowest=lowest)
+        assert np.array_equal(np.asarray([r["threshold"] for r in rows], dtype=np.float32), thr)
+        assert np.array_equal(maps.cpu().numpy(), want), metric
+        for i in (0, 7, 15):
+            y = orc.apply_assignment(x, want[i])
+            ex = orc.exact_metrics_f64(x, y)
+            for k in ("pcc", "mae", "atol"):
+                assert rows[i][k] == pytest.approx(ex[k], rel=1e-6, abs=1e-300), (metric, i, k)
+
+
+def test_wq_cli_writes_reference_artifacts(qa, tmp_path):
+    import json
+    from quantization_analysis_b200 import wq, synthetic
+    cfg = tmp_path / "cfg.json"
+    cfg.write_text(json.dumps({"algorithm": "mixed-tile-greedy", "quantization_formats": ["bf16", "bfp8", "bfp4", "bfp2", "fp0"],
+                               "params": {"metric": "pcc", "threshold": 0.999}, "seed": 123}))
+    rc = wq.run(["kv_a_proj", "--compression-config", str(cfg), "--out", str(tmp_path / "res")])
+    assert rc == 0
+    maps = list((tmp_path / "res").rglob("assignment.npy"))
+    assert len(maps) == 1
+    a = np.load(maps[0])
+    assert a.dtype == np.int8 and a.shape == (18, 224)
+    mapping = json.loads((maps[0].parent / "assignment_mapping.json").read_text())
+    assert mapping["int_to_format"] == G.MIXED and mapping["assignment_shape"] == [18, 224]
+    used = json.loads(next((tmp_path / "res").rglob("compression_config.used.json")).read_text())
+    assert used["seed"] == 123 and used["seed_source"] == "config"
+    # same map as the oracle's greedy on the same synthetic tensor
+    x = synthetic.randn_f32_np((576, 7168), 1000)
+    want, _ = orc.greedy_assign(orc.tile_stat_table(x), G.MIXED, "pcc", 0.999, 123)
+    assert np.array_equal(a, want)
+    assert next((tmp_path / "res").rglob("table.txt")).read_text().count("MIXED") == 1
+
+
+def test_striped_tables_concatenate_in_tile_order(qa):
+    """Row stripes (sharding.row_stripes) produce table slices that concatenate to the full table."""
+    from quantization_analysis_b200 import sharding
+    eng = qa["engine"]
+    x = G.algo_input("het_256x512")
+    full = eng.tile_stats(eng.prepare_tiles(x), G.MIXED)
+    parts = []
+    for a, b in sharding.row_stripes(x.shape[0], 3):
+        parts.append(eng.tile_stats(eng.prepare_tiles(x[a:b]), G.MIXED))
+    assert torch.equal(torch.cat(parts, dim=1), full)
