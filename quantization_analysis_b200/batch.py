@@ -18,11 +18,12 @@ MIXED = engine.MIXED_FORMATS
 
 class GreedyBatch:
     def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
-                 tile_formats=MIXED, n_streams: int = 4, device=None):
+                 tile_formats=MIXED, n_streams: int | None = None, device=None):
         self.device = device or engine._require_cuda()
         self.metric, self.threshold, self.seed = metric, float(threshold), int(seed)
         self.tile_formats = list(tile_formats)
         self.shapes = [tuple(int(v) for v in s) for s in shapes]
+        n_streams = min(16, len(self.shapes)) if n_streams is None else n_streams     # one stream per tensor
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
         L = _lib.lib()
         self.slots = []
