@@ -73,6 +73,7 @@ struct Sh {
     long long xl[2][MAXR][12];
     double xd[2][MAXR];
     int cnt[QA_NFMT];
+    unsigned long long mbar;     // cluster exchange barrier: one arrival per CTA per exchange
 };
 
 struct Coop {
@@ -80,17 +81,50 @@ struct Coop {
     cg::cluster_group cl;
     unsigned rank, nr;
     int gtid, gth;       // cluster-wide thread id / thread count
-    unsigned par;        // exchange parity (uniform)
+    unsigned par;        // exchange counter (uniform): low bit = payload buffer and mbarrier phase parity
     __device__ Coop(Sh& s) : sh(s), cl(cg::this_cluster()) {
         rank = cl.block_rank();
         nr = cl.num_blocks();
         gtid = (int)rank * GT + (int)threadIdx.x;
         gth = (int)nr * GT;
         par = 0;
+        if (nr > 1) {
+            if (threadIdx.x == 0) {
+                const uint32_t a = (uint32_t)__cvta_generic_to_shared(&sh.mbar);
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(nr));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            cl.sync();
+        }
     }
+    // full cluster barrier (global-memory phases): orders global writes and invalidates L1
     __device__ __forceinline__ void sync() {
         if (nr == 1) __syncthreads();
         else cl.sync();
+    }
+    // Payload exchange barrier.  Call pattern inside a collective: thread r (r < nr) has just stored this
+    // CTA's payload into CTA r's buffer `par & 1`; it then arrives on CTA r's mbarrier (release, cluster
+    // scope), and every thread waits until all nr CTAs have arrived on the local one (acquire).  About an
+    // order of magnitude cheaper than barrier.cluster with 16 x 512 threads.
+    __device__ __forceinline__ void xarrive_wait() {
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&sh.mbar);
+        if (threadIdx.x < nr) {
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(threadIdx.x));
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+        }
+        const uint32_t parity = par & 1u;
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(local), "r"(parity)
+                : "memory");
+        }
+        ++par;
     }
 };
 
@@ -123,9 +157,9 @@ __device__ __forceinline__ int c_scan_excl(Coop& c, int v, int& total) {
     int bt;
     const int ex = block_scan_excl(v, bt, c.sh);
     if (c.nr == 1) { total = bt; return ex; }
-    const unsigned b = c.par++ & 1u;
+    const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = bt;
-    c.cl.sync();
+    c.xarrive_wait();
     int base = 0, tot = 0;
     for (unsigned r = 0; r < c.nr; ++r) {
         const int x = c.sh.xi[b][r];
@@ -133,6 +167,30 @@ __device__ __forceinline__ int c_scan_excl(Coop& c, int v, int& total) {
         if (r < c.rank) base += x;
     }
     total = tot;
+    return base + ex;
+}
+
+// exclusive scan of v together with an OR-reduction of `flag`, one exchange
+__device__ __forceinline__ int c_scan_excl_any(Coop& c, int v, int& total, bool flag, bool& any) {
+    int bt;
+    const int blk = __syncthreads_or(flag ? 1 : 0);
+    const int ex = block_scan_excl(v, bt, c.sh);
+    if (c.nr == 1) { total = bt; any = blk != 0; return ex; }
+    const unsigned b = c.par & 1u;
+    if (threadIdx.x < c.nr) {
+        long long* dst = c.cl.map_shared_rank(&c.sh.xl[b][c.rank][0], threadIdx.x);
+        dst[0] = bt; dst[1] = blk;
+    }
+    c.xarrive_wait();
+    int base = 0, tot = 0, fl = 0;
+    for (unsigned r = 0; r < c.nr; ++r) {
+        const int x = (int)c.sh.xl[b][r][0];
+        tot += x;
+        fl |= (int)c.sh.xl[b][r][1];
+        if (r < c.rank) base += x;
+    }
+    total = tot;
+    any = fl != 0;
     return base + ex;
 }
 
@@ -145,9 +203,9 @@ __device__ __forceinline__ int c_min(Coop& c, int v) {
     for (int i = 1; i < NW; ++i) r = min(r, c.sh.i32[i]);
     __syncthreads();
     if (c.nr == 1) return r;
-    const unsigned b = c.par++ & 1u;
+    const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = r;
-    c.cl.sync();
+    c.xarrive_wait();
     int m = c.sh.xi[b][0];
     for (unsigned q = 1; q < c.nr; ++q) m = min(m, c.sh.xi[b][q]);
     return m;
@@ -156,9 +214,9 @@ __device__ __forceinline__ int c_min(Coop& c, int v) {
 __device__ __forceinline__ bool c_any(Coop& c, bool p) {
     const int blk = __syncthreads_or(p ? 1 : 0);
     if (c.nr == 1) return blk != 0;
-    const unsigned b = c.par++ & 1u;
+    const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = blk;
-    c.cl.sync();
+    c.xarrive_wait();
     int m = 0;
     for (unsigned q = 0; q < c.nr; ++q) m |= c.sh.xi[b][q];
     return m != 0;
@@ -182,9 +240,9 @@ __device__ __forceinline__ double c_reduce_d(Coop& c, double v) {
     }
     __syncthreads();
     if (c.nr == 1) return r;
-    const unsigned b = c.par++ & 1u;
+    const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xd[b][c.rank], threadIdx.x) = r;
-    c.cl.sync();
+    c.xarrive_wait();
     double t = c.sh.xd[b][0];
     for (unsigned q = 1; q < c.nr; ++q) t = MAX ? fmax(t, c.sh.xd[b][q]) : t + c.sh.xd[b][q];
     return t;
@@ -192,14 +250,16 @@ __device__ __forceinline__ double c_reduce_d(Coop& c, double v) {
 
 // One thread of the cluster (owner) publishes n <= 8 doubles to every CTA; all threads read them back.
 __device__ __forceinline__ void c_bcast_d(Coop& c, bool owner, const double* vals, int n, double* out) {
-    const unsigned b = c.par++ & 1u;
+    const unsigned b = c.par & 1u;
     if (owner) {
         for (unsigned r = 0; r < c.nr; ++r) {
             double* dst = c.nr == 1 ? &c.sh.xd[b][0] : c.cl.map_shared_rank(&c.sh.xd[b][0], r);
             for (int i = 0; i < n; ++i) dst[i] = vals[i];
         }
     }
-    c.sync();
+    __syncthreads();                 // the owner's stores happen-before this CTA's arrivals below
+    if (c.nr == 1) ++c.par;
+    else c.xarrive_wait();
     for (int i = 0; i < n; ++i) out[i] = c.sh.xd[b][i];
 }
 
@@ -301,13 +361,13 @@ __device__ __forceinline__ void scan_totals(Coop& c, const P2 (&tot)[NS], P2 (&p
         pre[s] = p2_then(pre[s], lanes_before);
     }
     if (c.nr > 1) {
-        const unsigned b = c.par++ & 1u;
+        const unsigned b = c.par & 1u;
         if (threadIdx.x < c.nr) {
             long long* dst = c.cl.map_shared_rank(&sh.xl[b][c.rank][0], threadIdx.x);
 #pragma unroll
             for (int s = 0; s < NS; ++s) { dst[2 * s] = sh.i64[(NW * NS + s) * 2]; dst[2 * s + 1] = sh.i64[(NW * NS + s) * 2 + 1]; }
         }
-        c.cl.sync();
+        c.xarrive_wait();
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             P2 cp{0, 0};
@@ -332,12 +392,12 @@ __device__ __forceinline__ void c_min3(Coop& c, int& v0, int& v1, int& v2) {
     for (int i = 1; i < NW; ++i) { r0 = min(r0, c.sh.i32[i]); r1 = min(r1, c.sh.i32[NW + i]); r2 = min(r2, (int)c.sh.i64[i]); }
     __syncthreads();
     if (c.nr > 1) {
-        const unsigned b = c.par++ & 1u;
+        const unsigned b = c.par & 1u;
         if (threadIdx.x < c.nr) {
             long long* dst = c.cl.map_shared_rank(&c.sh.xl[b][c.rank][0], threadIdx.x);
             dst[0] = r0; dst[1] = r1; dst[2] = r2;
         }
-        c.cl.sync();
+        c.xarrive_wait();
         for (unsigned q = 0; q < c.nr; ++q) {
             r0 = min(r0, (int)c.sh.xl[b][q][0]); r1 = min(r1, (int)c.sh.xl[b][q][1]); r2 = min(r2, (int)c.sh.xl[b][q][2]);
         }
@@ -483,14 +543,16 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
             if (p0 + j >= pnext) validmask |= 1u << j;
         // fixed point of c_in = exclusive_prefix(accepts(c_in)); thread 0 is right from the start and
         // every sweep fixes at least one more thread (typically all of them within ~10 sweeps)
-        int c_in = 0, total = 0, a = local_accepts(raw, validmask, 0, i_cur, L);
+        int c_in = 0, total = 0, a = local_accepts(raw, validmask, 0, i_cur, L), a_prev = -1;
         for (;;) {
-            const int c_new = c_scan_excl(c, a, total);
-            const int a_new = local_accepts(raw, validmask, c_new, i_cur, L);
-            const bool changed = (a_new != a) || (c_new != c_in);
-            a = a_new;
+            // one exchange per sweep: prefix of the accept counts + "did any count change since the last sweep";
+            // when none changed the prefix is the one the counts were computed from, i.e. the fixed point
+            bool any;
+            const int c_new = c_scan_excl_any(c, a, total, a != a_prev, any);
+            if (!any) break;
+            a_prev = a;
             c_in = c_new;
-            if (!c_any(c, changed)) break;
+            a = local_accepts(raw, validmask, c_in, i_cur, L);
         }
         // write j for the steps this thread resolved; find the draw that supplied the L-th accept
         int done_off = 0x7FFFFFFF;
@@ -863,6 +925,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             unsigned D = 0;
             int valid = len;
             P2 pre0[NS];
+            bool any_flag = guess;             // uniform: does any element of the chunk carry an accept flag?
             cy_load += clock64() - tq;
             for (int round = 0; round < 64; ++round) {
                 ++chain_rounds;
@@ -882,7 +945,11 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
 #pragma unroll
                     for (int s = 0; s < NS; ++s) tot[s] = p2_then(tot[s], p[s]);
                 }
-                scan_totals<NS>(c, tot, pre0);
+                if (any_flag) scan_totals<NS>(c, tot, pre0);
+                else {
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) pre0[s] = P2{0, 0};
+                }
                 cy_scan += clock64() - tq; tq = clock64();
                 // walk 2: exact state before every element -> decision; first wrong flag; first binade exit
                 int mism = 0x7FFFFFFF, cut = 0x7FFFFFFF;
@@ -918,8 +985,11 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                     }
                 }
                 cy_dec += clock64() - tq; tq = clock64();
-                int unused = 0x7FFFFFFF;
-                c_min3(c, mism, cut, unused);
+                // third slot: 0 if any element would carry an accept flag in the next round (F below mism, D from it on)
+                int next_any = 0x7FFFFFFF;
+                for (int j = 0; j < cnt && lo + j < valid; ++j)
+                    if ((D >> j) & 1u || (F >> j) & 1u) next_any = 0;
+                c_min3(c, mism, cut, next_any);
                 cy_min += clock64() - tq;
                 cut = min(cut, valid - 1);
                 if (mism > cut) { valid = cut + 1; break; }       // flags are consistent up to the cut
@@ -929,6 +999,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                     const int idx = lo + j;
                     if (idx >= mism && idx < valid) F = (F & ~(1u << j)) | (D & (1u << j));
                 }
+                any_flag = next_any == 0;       // conservative (a superset of the flags actually set)
                 if (round == 63) break;
             }
             // ---- commit [0, valid): D holds the decisions; pre0 the exact prefix of this thread ----
