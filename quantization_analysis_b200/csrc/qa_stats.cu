@@ -111,14 +111,15 @@ __device__ __forceinline__ void fmt_step(const float2 X, const float2 aX, GroupA
 
 template <bool EXACT_ABS>
 __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
-    // shared exponent: max of |bf16| patterns, two per word
-    uint32_t m = 0;
+    // shared exponent = exponent of max |x| (one 3-input max with |.| modifiers per word)
+    float2 xv[8];
+    float mabs = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint32_t v = w[i] & 0x7FFF7FFFu;
-        asm("max.u16x2 %0, %1, %2;" : "=r"(m) : "r"(m), "r"(v));
+        xv[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+        mabs = max3abs(mabs, xv[i].x, xv[i].y);
     }
-    const uint32_t E = max(m & 0xFFFFu, m >> 16) >> 7;
+    const uint32_t E = __float_as_uint(mabs) >> 23;
     if (E == 0u) return;                         // every element is zero/denormal: flushed (x ~ 0)
     if (E < 24u || E == 255u) {
         // rare: keep the caller's accumulators in registers by handing the slow path its own copy
@@ -148,7 +149,7 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     double gx = 0.0, gx2 = 0.0, gax = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const float2 x = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+        const float2 x = xv[i];
         // sum x, sum x^2 (and sum |x|): float64 per element - exact whatever the exponent spread
         const double x0 = (double)x.x, x1 = (double)x.y;
         gx += x0;
@@ -199,21 +200,30 @@ __device__ __forceinline__ void load_row_group(const uint16_t* __restrict__ x, i
     }
 }
 
-constexpr int FAST_WARPS = 4;
+constexpr int FAST_WARPS = 4;               // warps per CTA; one CTA = one 32-row x 512-column item
+constexpr int FAST_RPW = TILE / FAST_WARPS; // rows per warp
 constexpr int FAST_UNROLL = 4;
+#ifndef FAST_MIN_BLOCKS
+#define FAST_MIN_BLOCKS 4
+#endif
 
+// One CTA per (tile row, 512-column chunk); warp w walks rows 8w..8w+7 of the stripe, the four
+// partial accumulator sets are summed in warp order through shared memory (fixed order => the
+// result is deterministic, and exact whenever the float64 sums are representable).  Small items
+// keep the last wave short: o_proj is 7168 CTAs = 12 waves of 592 instead of 3.03 waves of big ones.
 template <bool VEC, bool EXACT_ABS>
-__global__ void __launch_bounds__(FAST_WARPS * 32) stats_fast_kernel(
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_kernel(
     const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
     int64_t chunks, int64_t nitems, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
-    const int lane = threadIdx.x & 31;
-    const int64_t item = (int64_t)blockIdx.x * FAST_WARPS + (threadIdx.x >> 5);
-    if (item >= nitems) return;
+    __shared__ double part[FAST_WARPS - 1][14][32];
+    __shared__ float partmx[FAST_WARPS - 1][3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t item = blockIdx.x;
     const int64_t tr = item / chunks;
     const int64_t ck = item - tr * chunks;
     const int64_t col0 = ck * 512 + (int64_t)lane * GROUP;
-    const int64_t row0 = tr * TILE;
-    const int nrows = (int)min((int64_t)TILE, rows - row0);
+    const int64_t row0 = tr * TILE + w * FAST_RPW;
+    const int nrows = (int)max((int64_t)0, min((int64_t)FAST_RPW, rows - row0));
     TileAcc a;
     acc_zero(a);
     if (col0 < cols) {
@@ -232,6 +242,27 @@ __global__ void __launch_bounds__(FAST_WARPS * 32) stats_fast_kernel(
     }
 #pragma unroll
     for (int f = 0; f < 3; ++f) a.sxy[f] += a.sy2[f];    // sum x*y = sum y^2 + sum (x-y)*y
+    if (w > 0) {
+        double (*p)[32] = part[w - 1];
+        p[0][lane] = a.sx; p[1][lane] = a.sx2;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            p[2 + f][lane] = a.sy[f]; p[5 + f][lane] = a.sy2[f]; p[8 + f][lane] = a.sxy[f]; p[11 + f][lane] = a.sab[f];
+            partmx[w - 1][f][lane] = a.amax[f];
+        }
+    }
+    __syncthreads();
+    if (w != 0) return;
+#pragma unroll
+    for (int q = 0; q < FAST_WARPS - 1; ++q) {
+        a.sx += part[q][0][lane]; a.sx2 += part[q][1][lane];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            a.sy[f] += part[q][2 + f][lane]; a.sy2[f] += part[q][5 + f][lane];
+            a.sxy[f] += part[q][8 + f][lane]; a.sab[f] += part[q][11 + f][lane];
+            a.amax[f] = fmaxf(a.amax[f], partmx[q][f][lane]);
+        }
+    }
     // lanes 2j and 2j+1 hold the two halves of tile j
     a.sx += shfl_xor_d(a.sx, 1);
     a.sx2 += shfl_xor_d(a.sx2, 1);
@@ -458,7 +489,7 @@ extern "C" int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t c
     if (mode == QA_STATS_FAST || mode == QA_STATS_FAST_APPROX_ABS) {
         if (x_dtype != QA_DT_BF16) { set_error("qa_tile_stats: fast mode needs bf16 input (use QA_STATS_STRICT for fp32)"); return 1; }
         const int64_t chunks = cdiv(cols, 512), nitems = tiles_h * chunks;
-        const int64_t grid = cdiv(nitems, FAST_WARPS);
+        const int64_t grid = nitems;
         const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
         const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
         const bool exact_abs = (mode == QA_STATS_FAST);
