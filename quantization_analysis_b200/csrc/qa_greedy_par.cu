@@ -263,6 +263,36 @@ __device__ __forceinline__ void c_bcast_d(Coop& c, bool owner, const double* val
     for (int i = 0; i < n; ++i) out[i] = c.sh.xd[b][i];
 }
 
+// c_bcast_d plus a cluster-wide sum of one double per thread (CTA partials in rank order), one exchange
+__device__ __forceinline__ double c_bcast_sum_d(Coop& c, bool owner, const double* vals, int n, double* out, double part) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+        part += __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(part), o),
+                                 __shfl_xor_sync(0xFFFFFFFFu, __double2loint(part), o));
+    if ((threadIdx.x & 31) == 0) c.sh.i64[threadIdx.x >> 5] = __double_as_longlong(part);
+    const unsigned b = c.par & 1u;
+    if (owner) {
+        for (unsigned r = 0; r < c.nr; ++r) {
+            double* dst = c.nr == 1 ? &c.sh.xd[b][0] : c.cl.map_shared_rank(&c.sh.xd[b][0], r);
+            for (int i = 0; i < n; ++i) dst[i] = vals[i];
+        }
+    }
+    __syncthreads();
+    double blk = 0.0;
+    for (int i = 0; i < NW; ++i) blk += __longlong_as_double(c.sh.i64[i]);
+    double tot = blk;
+    if (c.nr == 1) ++c.par;
+    else {
+        if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xl[b][c.rank][0], threadIdx.x) = __double_as_longlong(blk);
+        c.xarrive_wait();
+        tot = 0.0;
+        for (unsigned r = 0; r < c.nr; ++r) tot += __longlong_as_double(c.sh.xl[b][r][0]);
+    }
+    for (int i = 0; i < n; ++i) out[i] = c.sh.xd[b][i];
+    __syncthreads();
+    return tot;
+}
+
 // ---------------------------------------------------------------------------------------------
 // sequentially-rounded float64 accumulation as a scan
 // ---------------------------------------------------------------------------------------------
@@ -276,18 +306,41 @@ __device__ __forceinline__ P2 p2_then(P2 a, P2 b) {   // apply a, then b
 struct Grid {        // binade of the running sum at the start of a chunk
     double q;        // ulp (power of two); 0 => no grid (S == 0, inf/nan or denormal range)
     double invq;
-    long long m0;    // |S| / q, in [2^52, 2^53)
+    long long m0;    // |S| / q, in [2^52, 2^53)   (relaxed: S / q, signed, |m0| < 2^52)
     double sign;     // +1 / -1
+    bool relaxed;    // fixed coarser grid that cannot be left: accurate (<= 1 ulp of the bound) but not the
+                     // reference's rounding sequence; used for a signed sum that would hop between binades
 };
 __device__ __forceinline__ Grid make_grid(double S) {
     Grid g;
     const int e = (int)((__double2hiint(S) >> 20) & 0x7FF);
+    g.relaxed = false;
     if (e < 64 || e > 1900) { g.q = 0.0; g.invq = 0.0; g.m0 = 0; g.sign = 1.0; return g; }
     g.q = __hiloint2double((e - 52) << 20, 0);
     g.invq = __hiloint2double((1023 + 1023 + 52 - e) << 20, 0);
     g.sign = S < 0.0 ? -1.0 : 1.0;
     g.m0 = __double2ll_rn(fabs(S) * g.invq);
     return g;
+}
+// grid of the binade above |S| + bound: every state reachable by adding terms of total magnitude <= bound stays on it
+__device__ __forceinline__ Grid make_grid_relaxed(double S, double bound) {
+    Grid g;
+    const double top = 2.0 * (fabs(S) + bound);
+    int e = (int)((__double2hiint(top) >> 20) & 0x7FF);
+    if (e < 64) e = 64;
+    g.relaxed = true;
+    g.sign = 1.0;
+    if (e > 1900) { g.q = 0.0; g.invq = 0.0; g.m0 = 0; return g; }
+    g.q = __hiloint2double((e - 52) << 20, 0);
+    g.invq = __hiloint2double((1023 + 1023 + 52 - e) << 20, 0);
+    g.m0 = __double2ll_rn(S * g.invq);
+    return g;
+}
+// true when S +/- bound provably stays inside the binade of S (no grid change possible)
+__device__ __forceinline__ bool stays_in_binade(double S, double bound) {
+    const double lo = fabs(S) - bound, hi = fabs(S) + bound;
+    if (!(lo > 0.0)) return false;
+    return ((__double2hiint(lo) >> 20) & 0x7FF) == ((__double2hiint(hi) >> 20) & 0x7FF);
 }
 // classify one addend: returns false when it cannot be expressed on the grid (caller cuts the chunk)
 __device__ __forceinline__ bool classify(const Grid& g, double t, P2& out) {
@@ -307,6 +360,7 @@ __device__ __forceinline__ bool classify(const Grid& g, double t, P2& out) {
 __device__ __forceinline__ long long m_after(const Grid& g, P2 p) { return g.m0 + ((g.m0 & 1ll) ? p.d1 : p.d0); }
 __device__ __forceinline__ double s_of(const Grid& g, long long m) { return g.sign * ((double)m * g.q); }
 __device__ __forceinline__ bool in_binade(long long m) { return m >= M_LO && m < M_HI; }
+__device__ __forceinline__ bool left_grid(const Grid& g, long long m) { return g.q != 0.0 && !g.relaxed && !in_binade(m); }
 
 __device__ __forceinline__ P2 shfl_up_p2(P2 v, int o) {
     P2 y;
@@ -823,7 +877,10 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     const int tid = threadIdx.x;
     const int base = ord.fmt[0];
     constexpr bool is_pcc = PCC;
-    constexpr int NS = PCC ? 4 : 1;       // running sums that drive the decision: sy, sy2, sxy, sabs | sabs
+    // running sums carried with the reference's exact rounding sequence: sy, sy2, sxy (pcc) | sabs (mae).
+    // In pcc mode sum|x-y| only enters the degenerate den == 0 branch (mixed_tile_greedy.py:187-188): it is
+    // tracked as a plain per-chunk sum (it starts at 0 and would change binade ~40 times on its way up).
+    constexpr int NS = PCC ? 3 : 1;
     constexpr int S0 = PCC ? 0 : 3;       // first table statistic among them
     for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
     if (tid < QA_NFMT) sh.cnt[tid] = 0;
@@ -847,10 +904,23 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             faithful_init_sums<4>(c, cols, nt, R, dg, 1 << 30);
             k.sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
         }
-        {   // signed sums (means): faithful unless they keep hopping between binades
+        {   // signed sums (means).  A sum with heavy cancellation (|sum t| << sum |t|: zero-mean weights) is a
+            // random walk that changes binade all the time; it goes straight to a fixed-order tree sum and is
+            // flagged (its rounding differences are ~1e-16 of a term that enters bm2 at the 1e-7 level).
+            // Otherwise it is carried with the reference's rounding sequence like the other columns.
             const double* const cols[2] = {table + (size_t)QA_STAT_SX * nt, table + (size_t)QA_STAT_FMT(base, 0) * nt};
             double R[2];
-            faithful_init_sums<2>(c, cols, nt, R, degraded, 24);
+            bool walk[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                double sm = 0.0, sa = 0.0;
+                for (int i = c.gtid; i < nt; i += c.gth) { const double v = cols[q][i]; sm += v; sa += fabs(v); }
+                R[q] = c_reduce_d<false>(c, sm);
+                sa = c_reduce_d<false>(c, sa);
+                walk[q] = fabs(R[q]) < 0.25 * sa;
+            }
+            if (walk[0] && walk[1]) degraded = 3u;
+            else faithful_init_sums<2>(c, cols, nt, R, degraded, 24);
             k.sx = R[0]; S[0] = R[1];
         }
     } else {
@@ -864,6 +934,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     unsigned chain_rounds = 0;
     long long t_mark = clock64(), cyc_perm = 0, cyc_chain = 0;
     long long cy_load = 0, cy_scan = 0, cy_dec = 0, cy_min = 0, cy_commit = 0, cy_gather = 0, tq = 0;
+    unsigned n_chunks = 0, n_cutshort = 0;
     const long long cyc_init = t_mark - t_start;
     const int CHc = c.gth * EPS;
 
@@ -902,13 +973,26 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         const int prev = ord.fmt[fi - 1];
         double* dq[4] = {w.dbuf, w.dbuf + (size_t)nt, w.dbuf + 2 * (size_t)nt, w.dbuf + 3 * (size_t)nt};
         tq = clock64();
+        double drift = 0.0;                              // sum |delta sy| of the pass: how far sy can move
         for (int q = c.gtid; q < m; q += c.gth) {      // gather the deltas once, in visiting order
             const int t = w.order[q];
 #pragma unroll
             for (int s = 0; s < NS; ++s)
                 dq[s][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, S0 + s) * nt + t], table[(size_t)QA_STAT_FMT(prev, S0 + s) * nt + t]);
+            if (PCC) {
+                dq[3][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, 3) * nt + t], table[(size_t)QA_STAT_FMT(prev, 3) * nt + t]);
+                drift += fabs(dq[0][q]);
+            }
         }
         c.sync();
+        // sy is a signed sum near its mean: if the pass could carry it across a binade boundary (or zero),
+        // run it on a fixed coarser grid instead of cutting a chunk at every hop
+        bool relax_sy = false;
+        if (PCC) {
+            drift = c_reduce_d<false>(c, drift);
+            relax_sy = !stays_in_binade(S[0], drift);
+            if (relax_sy) degraded |= 4u;
+        }
         cy_gather += clock64() - tq;
         // ---- (3) accept / reject chain -------------------------------------------------------
         int pos = 0;
@@ -920,7 +1004,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             tq = clock64();
             Grid gr[NS];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) gr[s] = make_grid(S[S0 + s]);
+            for (int s = 0; s < NS; ++s) gr[s] = (PCC && s == 0 && relax_sy) ? make_grid_relaxed(S[0], drift) : make_grid(S[S0 + s]);
             unsigned F = guess && cnt > 0 ? (0xFFFFFFFFu >> (32 - cnt)) : 0u;     // accept flags, bit j <-> element lo + j
             unsigned D = 0;
             int valid = len;
@@ -967,6 +1051,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                             const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
                             cnd[S0 + s] = __dadd_rn(sb, dl[s]);
                         }
+                        if (PCC) cnd[3] = S[3] + dq[3][pos + idx];      // chunk-start value: only its zero test matters
                         const bool dj = good_par(k, cnd);
                         const bool fj = (F >> j) & 1u;
                         D |= dj ? (1u << j) : 0u;
@@ -978,7 +1063,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                                 P2 p{0, 0};
                                 classify(gr[s], dl[s], p);
                                 run[s] = p2_then(run[s], p);
-                                if (gr[s].q != 0.0 && !in_binade(m_after(gr[s], run[s]))) cut = min(cut, idx);
+                                if (left_grid(gr[s], m_after(gr[s], run[s]))) cut = min(cut, idx);
                             }
                             if (cut == idx) break;
                         }
@@ -1007,10 +1092,14 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             int loc = 0;
             bool owner = false;
             double vals[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double dabs = 0.0;
             for (int j = 0; j < cnt && lo + j < valid; ++j) {
                 const int t = w.order[pos + lo + j];
-                if ((D >> j) & 1u) { assignment[t] = (int8_t)fmt; ++loc; }
-                else w.fixed[t] = 1;
+                if ((D >> j) & 1u) {
+                    assignment[t] = (int8_t)fmt;
+                    ++loc;
+                    if (PCC) dabs += dq[3][pos + lo + j];
+                } else w.fixed[t] = 1;
             }
             if (valid - 1 >= lo && valid - 1 < lo + EPS) {       // owner of the last committed element
                 owner = true;
@@ -1038,10 +1127,13 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             loc = __reduce_add_sync(0xFFFFFFFFu, loc);
             if ((tid & 31) == 0 && loc) { atomicAdd(&sh.cnt[fmt], loc); atomicAdd(&sh.cnt[prev], -loc); }
             double nv[5];
-            c_bcast_d(c, owner, vals, 5, nv);
+            const double dabs_all = c_bcast_sum_d(c, owner, vals, 5, nv, dabs);
 #pragma unroll
             for (int s = 0; s < NS; ++s) S[S0 + s] = nv[S0 + s];
+            if (PCC) S[3] += dabs_all;
             guess = nv[4] != 0.0;
+            ++n_chunks;
+            if (valid < len) ++n_cutshort;
             pos += valid;
             cy_commit += clock64() - tq;
         }
@@ -1065,6 +1157,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[12] = (double)c.nr;
         state[13] = (double)cy_load + 1e-9 * 0; state[14] = (double)cy_scan; state[15] = (double)cy_dec;
         state[16] = (double)cy_min; state[17] = (double)cy_commit; state[18] = (double)cy_gather;
+        state[19] = (double)n_chunks; state[20] = (double)n_cutshort;
     }
 }
 

@@ -142,10 +142,16 @@ def test_parallel_greedy_equals_sequential_chain(qa):
             assert torch.equal(r1, r2)
             s1, s2 = s1.cpu().numpy(), s2.cpu().numpy()
             flags = int(s2[6]) & 0xFFFF
-            sel = [1, 3, 4, 5, 7] if metric == "pcc" else [5, 7]
+            # sequentially rounded sums that drive the decisions are bit-identical; in pcc mode sum|x-y| is a
+            # plain sum (only its zero test is ever used) and sum x / sum y may be flagged as tree / fixed-grid sums
+            sel = [1, 3, 4, 7] if metric == "pcc" else [5, 7]
             assert np.array_equal(s1[sel], s2[sel]), (metric, s1, s2)
-            if metric == "pcc" and not (flags & 3):
-                assert np.array_equal(s1[[0, 2]], s2[[0, 2]])
+            if metric == "pcc":
+                assert s2[5] == pytest.approx(s1[5], rel=1e-12)
+                if not (flags & 7):
+                    assert np.array_equal(s1[[0, 2]], s2[[0, 2]])
+                else:
+                    assert np.allclose(s1[[0, 2]], s2[[0, 2]], rtol=1e-12, atol=1e-9)
 
 
 @pytest.mark.parametrize("strict", [False, True])
