@@ -274,9 +274,14 @@ def main() -> None:
          "launches_per_step": len(batch.slots), "alg_bytes_per_step": alg_assign,
          "achieved_gbs": alg_assign / (ms_assign * 1e-3) / 1e9},
     ]
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the o_proj tensor, 117.4 M elements), from the
+    # `ncu --set full` capture summarised in profiles/r1_summary.md (algorithmic bytes of that launch: stats
+    # 234.9 MB + 20.2 MB table = 255.1 MB; greedy 20.2 MB table + 0.1 MB map)
+    ncu_traffic = {"stats_fast_kernel": 234932224 + 16146944, "greedy_par_kernel": 18241792 + 74752}
     dom = max(kernels, key=lambda k: k["ms_per_step"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": dom["achieved_gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": dom["achieved_gbs"] / peak, "traffic": ncu_traffic.get(dom["kernel"]),
+                "traffic_note": "ncu dram bytes of the largest launch (o_proj); see profiles/r1_summary.md", "peak_source": peak_src,
                 "alg_bytes_per_launch": dom["alg_bytes_per_step"] / dom["launches_per_step"],
                 "avg_launch_ms": dom["ms_per_step"] / dom["launches_per_step"],
                 "note": "dominant kernel by time in the step; per-kernel breakdown in roofline_by_kernel"}
