@@ -120,6 +120,10 @@ int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int 
 int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* work,
                              qa_stream_t stream);
 
+/* Diagnostic: cycles per call of the cluster collectives used by qa_greedy_assign_par
+ * (out double[8] on device: scan+flag exchange, 3-way min, cluster.sync, __syncthreads, pair scan). */
+int qa_collective_bench(double* out, int iters, int cluster, qa_stream_t stream);
+
 /* Per-tile threshold assignment for nthr thresholds at once.
  * Replaces mixed_tile_threshold.py:111-123 and scripts/sweep_mixed_tile_threshold.py:145-155.
  * scores: float32[QA_NFMT][ntiles] of ONE metric; order[norder]: formats by ascending bytes;

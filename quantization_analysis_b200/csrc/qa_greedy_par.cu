@@ -65,7 +65,7 @@ struct P2 {          // increment of m if the incoming m is even / odd
 };
 
 struct Sh {
-    int i32[2 * NW + 8];
+    int i32[3 * NW + 8];
     long long i64[NW * 6 * 2 + 16];
     double f64[16];
     // cluster exchange (double buffered; written by remote CTAs through DSMEM)
@@ -82,6 +82,7 @@ struct Coop {
     unsigned rank, nr;
     int gtid, gth;       // cluster-wide thread id / thread count
     unsigned par;        // exchange counter (uniform): low bit = payload buffer and mbarrier phase parity
+    long long cy_resolve = 0, cy_apply = 0; unsigned n_sweeps = 0, n_rounds = 0;   // diagnostics
     __device__ Coop(Sh& s) : sh(s), cl(cg::this_cluster()) {
         rank = cl.block_rank();
         nr = cl.num_blocks();
@@ -107,6 +108,11 @@ struct Coop {
     // scope), and every thread waits until all nr CTAs have arrived on the local one (acquire).  About an
     // order of magnitude cheaper than barrier.cluster with 16 x 512 threads.
     __device__ __forceinline__ void xarrive_wait() {
+#ifdef QA_XCHG_CLUSTER_SYNC
+        cl.sync();
+        ++par;
+        return;
+#endif
         const uint32_t local = (uint32_t)__cvta_generic_to_shared(&sh.mbar);
         if (threadIdx.x < nr) {
             uint32_t remote;
@@ -131,46 +137,52 @@ struct Coop {
 // ---------------------------------------------------------------------------------------------
 // block / cluster collectives (every thread of the cluster calls them, values come back uniform)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_scan_excl(int v, int& total, Sh& sh) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
+// warp-level helpers over a small array held one entry per lane
+__device__ __forceinline__ int lanes_incl_scan(int x) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += y;
+        const int y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
     }
+    return x;
+}
+
+__device__ __forceinline__ int block_scan_excl(int v, int& total, Sh& sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inc = lanes_incl_scan(v);
     if (lane == 31) sh.i32[w] = inc;
     __syncthreads();
-    int pre = 0, tot = 0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-        const int x = sh.i32[i];
-        tot += x;
-        if (i < w) pre += x;
-    }
-    total = tot;
+    // every warp scans the NW warp totals itself (one entry per lane)
+    const int wt = lanes_incl_scan(lane < NW ? sh.i32[lane] : 0);
+    total = __shfl_sync(0xFFFFFFFFu, wt, NW - 1);
+    const int before = __shfl_sync(0xFFFFFFFFu, wt, (w + 31) & 31);     // inclusive total of warp w-1
     __syncthreads();
-    return pre + inc - v;
+    return (w ? before : 0) + inc - v;
+}
+
+// exchange of one int per CTA; returns (sum over CTAs before this one, sum over all); entries read one per lane
+__device__ __forceinline__ void xchg_prefix(Coop& c, int mine, int& base, int& total) {
+    const unsigned b = c.par & 1u;
+    if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = mine;
+    c.xarrive_wait();
+    const int lane = threadIdx.x & 31;
+    const int sc = lanes_incl_scan(lane < (int)c.nr ? c.sh.xi[b][lane] : 0);
+    total = __shfl_sync(0xFFFFFFFFu, sc, c.nr - 1);
+    const int before = __shfl_sync(0xFFFFFFFFu, sc, (c.rank + 31) & 31);
+    base = c.rank ? before : 0;
 }
 
 __device__ __forceinline__ int c_scan_excl(Coop& c, int v, int& total) {
     int bt;
     const int ex = block_scan_excl(v, bt, c.sh);
     if (c.nr == 1) { total = bt; return ex; }
-    const unsigned b = c.par & 1u;
-    if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = bt;
-    c.xarrive_wait();
-    int base = 0, tot = 0;
-    for (unsigned r = 0; r < c.nr; ++r) {
-        const int x = c.sh.xi[b][r];
-        tot += x;
-        if (r < c.rank) base += x;
-    }
-    total = tot;
+    int base;
+    xchg_prefix(c, bt, base, total);
     return base + ex;
 }
 
-// exclusive scan of v together with an OR-reduction of `flag`, one exchange
+// exclusive scan of v together with an OR-reduction of `flag`, one exchange (flag rides in bit 30 of the CTA total)
 __device__ __forceinline__ int c_scan_excl_any(Coop& c, int v, int& total, bool flag, bool& any) {
     int bt;
     const int blk = __syncthreads_or(flag ? 1 : 0);
@@ -178,37 +190,31 @@ __device__ __forceinline__ int c_scan_excl_any(Coop& c, int v, int& total, bool 
     if (c.nr == 1) { total = bt; any = blk != 0; return ex; }
     const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) {
-        long long* dst = c.cl.map_shared_rank(&c.sh.xl[b][c.rank][0], threadIdx.x);
-        dst[0] = bt; dst[1] = blk;
+        int* dst = c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x);
+        *dst = bt | (blk ? (1 << 30) : 0);
     }
     c.xarrive_wait();
-    int base = 0, tot = 0, fl = 0;
-    for (unsigned r = 0; r < c.nr; ++r) {
-        const int x = (int)c.sh.xl[b][r][0];
-        tot += x;
-        fl |= (int)c.sh.xl[b][r][1];
-        if (r < c.rank) base += x;
-    }
-    total = tot;
-    any = fl != 0;
-    return base + ex;
+    const int lane = threadIdx.x & 31;
+    const int raw = lane < (int)c.nr ? c.sh.xi[b][lane] : 0;
+    any = __any_sync(0xFFFFFFFFu, (raw >> 30) & 1);
+    const int sc = lanes_incl_scan(raw & ~(1 << 30));
+    total = __shfl_sync(0xFFFFFFFFu, sc, c.nr - 1);
+    const int before = __shfl_sync(0xFFFFFFFFu, sc, (c.rank + 31) & 31);
+    return (c.rank ? before : 0) + ex;
 }
 
 __device__ __forceinline__ int c_min(Coop& c, int v) {
+    const int lane = threadIdx.x & 31;
     v = __reduce_min_sync(0xFFFFFFFFu, v);
-    if ((threadIdx.x & 31) == 0) c.sh.i32[threadIdx.x >> 5] = v;
+    if (lane == 0) c.sh.i32[threadIdx.x >> 5] = v;
     __syncthreads();
-    int r = c.sh.i32[0];
-#pragma unroll
-    for (int i = 1; i < NW; ++i) r = min(r, c.sh.i32[i]);
+    int r = __reduce_min_sync(0xFFFFFFFFu, lane < NW ? c.sh.i32[lane] : 0x7FFFFFFF);
     __syncthreads();
     if (c.nr == 1) return r;
     const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = r;
     c.xarrive_wait();
-    int m = c.sh.xi[b][0];
-    for (unsigned q = 1; q < c.nr; ++q) m = min(m, c.sh.xi[b][q]);
-    return m;
+    return __reduce_min_sync(0xFFFFFFFFu, lane < (int)c.nr ? c.sh.xi[b][lane] : 0x7FFFFFFF);
 }
 
 __device__ __forceinline__ bool c_any(Coop& c, bool p) {
@@ -217,9 +223,8 @@ __device__ __forceinline__ bool c_any(Coop& c, bool p) {
     const unsigned b = c.par & 1u;
     if (threadIdx.x < c.nr) *c.cl.map_shared_rank(&c.sh.xi[b][c.rank], threadIdx.x) = blk;
     c.xarrive_wait();
-    int m = 0;
-    for (unsigned q = 0; q < c.nr; ++q) m |= c.sh.xi[b][q];
-    return m != 0;
+    const int lane = threadIdx.x & 31;
+    return __any_sync(0xFFFFFFFFu, lane < (int)c.nr ? c.sh.xi[b][lane] : 0);
 }
 
 // deterministic cluster-wide float64 sum / max (fixed tree: lanes, warps in order, CTAs in order)
@@ -369,81 +374,118 @@ __device__ __forceinline__ P2 shfl_up_p2(P2 v, int o) {
     return y;
 }
 
+__device__ __forceinline__ long long lanes_incl_scan64(long long x) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    return x;
+}
+
 // Exclusive cluster-wide scan (cluster thread order) of one P2 per stream per thread.
+// Exact ties are rare (the addend must end exactly half an ulp of the running sum): a CTA whose elements are all
+// tie-free has state-independent increments (d0 == d1) and scans plain int64 sums; only a CTA that saw a tie runs
+// the pair scan.  CTA totals are exchanged as pairs either way and composed in rank order.
 template <int NS>
 __device__ __forceinline__ void scan_totals(Coop& c, const P2 (&tot)[NS], P2 (&pre)[NS]) {
     Sh& sh = c.sh;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    P2 inc[NS];
+    bool tie = false;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        inc[s] = tot[s];
+    for (int s = 0; s < NS; ++s) tie = tie || (tot[s].d0 != tot[s].d1);
+    P2 ctot[NS];
+    if (!__syncthreads_or(tie ? 1 : 0)) {
+        long long inc[NS];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const P2 y = shfl_up_p2(inc[s], o);
-            if (lane >= o) inc[s] = p2_then(y, inc[s]);
+        for (int s = 0; s < NS; ++s) {
+            inc[s] = lanes_incl_scan64(tot[s].d0);
+            if (lane == 31) sh.i64[w * NS + s] = inc[s];
         }
-        if (lane == 31) { sh.i64[(w * NS + s) * 2] = inc[s].d0; sh.i64[(w * NS + s) * 2 + 1] = inc[s].d1; }
-    }
-    __syncthreads();
-    // warp 0 turns the NW warp totals into exclusive prefixes (+ the CTA total in slot NW)
-    if (w == 0) {
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const long long wt = lanes_incl_scan64(lane < NW ? sh.i64[lane * NS + s] : 0ll);
+            const long long all = __shfl_sync(0xFFFFFFFFu, wt, NW - 1);
+            const long long before = __shfl_sync(0xFFFFFFFFu, wt, (w + 31) & 31);
+            const long long v = (w ? before : 0ll) + inc[s] - tot[s].d0;
+            pre[s] = P2{v, v};
+            ctot[s] = P2{all, all};
+        }
+        __syncthreads();
+    } else {
+        P2 inc[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            inc[s] = tot[s];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const P2 y = shfl_up_p2(inc[s], o);
+                if (lane >= o) inc[s] = p2_then(y, inc[s]);
+            }
+            if (lane == 31) { sh.i64[(w * NS + s) * 2] = inc[s].d0; sh.i64[(w * NS + s) * 2 + 1] = inc[s].d1; }
+        }
+        __syncthreads();
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             P2 t{0, 0};
             if (lane < NW) { t.d0 = sh.i64[(lane * NS + s) * 2]; t.d1 = sh.i64[(lane * NS + s) * 2 + 1]; }
-            P2 ti = t;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const P2 y = shfl_up_p2(ti, o);
-                if (lane >= o) ti = p2_then(y, ti);
+                const P2 y = shfl_up_p2(t, o);
+                if (lane >= o) t = p2_then(y, t);
             }
-            P2 te = shfl_up_p2(ti, 1);
-            if (lane == 0) te = P2{0, 0};
-            __syncwarp();
-            if (lane < NW) { sh.i64[(lane * NS + s) * 2] = te.d0; sh.i64[(lane * NS + s) * 2 + 1] = te.d1; }
-            if (lane == NW - 1) { sh.i64[(NW * NS + s) * 2] = ti.d0; sh.i64[(NW * NS + s) * 2 + 1] = ti.d1; }
+            P2 before, all;
+            before.d0 = __shfl_sync(0xFFFFFFFFu, t.d0, (w + 31) & 31);
+            before.d1 = __shfl_sync(0xFFFFFFFFu, t.d1, (w + 31) & 31);
+            all.d0 = __shfl_sync(0xFFFFFFFFu, t.d0, NW - 1);
+            all.d1 = __shfl_sync(0xFFFFFFFFu, t.d1, NW - 1);
+            if (w == 0) before = P2{0, 0};
+            P2 lanes_before = shfl_up_p2(inc[s], 1);
+            if (lane == 0) lanes_before = P2{0, 0};
+            pre[s] = p2_then(before, lanes_before);
+            ctot[s] = all;
         }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        pre[s].d0 = sh.i64[(w * NS + s) * 2];
-        pre[s].d1 = sh.i64[(w * NS + s) * 2 + 1];
-        P2 lanes_before = shfl_up_p2(inc[s], 1);
-        if (lane == 0) lanes_before = P2{0, 0};
-        pre[s] = p2_then(pre[s], lanes_before);
+        __syncthreads();
     }
     if (c.nr > 1) {
         const unsigned b = c.par & 1u;
         if (threadIdx.x < c.nr) {
             long long* dst = c.cl.map_shared_rank(&sh.xl[b][c.rank][0], threadIdx.x);
 #pragma unroll
-            for (int s = 0; s < NS; ++s) { dst[2 * s] = sh.i64[(NW * NS + s) * 2]; dst[2 * s + 1] = sh.i64[(NW * NS + s) * 2 + 1]; }
+            for (int s = 0; s < NS; ++s) { dst[2 * s] = ctot[s].d0; dst[2 * s + 1] = ctot[s].d1; }
         }
         c.xarrive_wait();
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            P2 cp{0, 0};
-            for (unsigned r = 0; r < c.rank; ++r) cp = p2_then(cp, P2{sh.xl[b][r][2 * s], sh.xl[b][r][2 * s + 1]});
+            P2 t{0, 0};
+            if (lane < (int)c.nr) { t.d0 = sh.xl[b][lane][2 * s]; t.d1 = sh.xl[b][lane][2 * s + 1]; }
+#pragma unroll
+            for (int o = 1; o < MAXR; o <<= 1) {
+                const P2 y = shfl_up_p2(t, o);
+                if (lane >= o) t = p2_then(y, t);
+            }
+            P2 cp;
+            cp.d0 = __shfl_sync(0xFFFFFFFFu, t.d0, (c.rank + 31) & 31);
+            cp.d1 = __shfl_sync(0xFFFFFFFFu, t.d1, (c.rank + 31) & 31);
+            if (c.rank == 0) cp = P2{0, 0};
             pre[s] = p2_then(cp, pre[s]);
         }
-    } else {
-        __syncthreads();
     }
 }
 
 // three cluster-wide minima in one exchange
 __device__ __forceinline__ void c_min3(Coop& c, int& v0, int& v1, int& v2) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     v0 = __reduce_min_sync(0xFFFFFFFFu, v0);
     v1 = __reduce_min_sync(0xFFFFFFFFu, v1);
     v2 = __reduce_min_sync(0xFFFFFFFFu, v2);
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { c.sh.i32[w] = v0; c.sh.i32[NW + w] = v1; c.sh.i64[w] = v2; }
+    if (lane == 0) { c.sh.i32[w] = v0; c.sh.i32[NW + w] = v1; c.sh.i32[2 * NW + w] = v2; }
     __syncthreads();
-    int r0 = c.sh.i32[0], r1 = c.sh.i32[NW], r2 = (int)c.sh.i64[0];
-#pragma unroll
-    for (int i = 1; i < NW; ++i) { r0 = min(r0, c.sh.i32[i]); r1 = min(r1, c.sh.i32[NW + i]); r2 = min(r2, (int)c.sh.i64[i]); }
+    int r0 = __reduce_min_sync(0xFFFFFFFFu, lane < NW ? c.sh.i32[lane] : 0x7FFFFFFF);
+    int r1 = __reduce_min_sync(0xFFFFFFFFu, lane < NW ? c.sh.i32[NW + lane] : 0x7FFFFFFF);
+    int r2 = __reduce_min_sync(0xFFFFFFFFu, lane < NW ? c.sh.i32[2 * NW + lane] : 0x7FFFFFFF);
     __syncthreads();
     if (c.nr > 1) {
         const unsigned b = c.par & 1u;
@@ -452,9 +494,10 @@ __device__ __forceinline__ void c_min3(Coop& c, int& v0, int& v1, int& v2) {
             dst[0] = r0; dst[1] = r1; dst[2] = r2;
         }
         c.xarrive_wait();
-        for (unsigned q = 0; q < c.nr; ++q) {
-            r0 = min(r0, (int)c.sh.xl[b][q][0]); r1 = min(r1, (int)c.sh.xl[b][q][1]); r2 = min(r2, (int)c.sh.xl[b][q][2]);
-        }
+        const bool on = lane < (int)c.nr;
+        r0 = __reduce_min_sync(0xFFFFFFFFu, on ? (int)c.sh.xl[b][lane][0] : 0x7FFFFFFF);
+        r1 = __reduce_min_sync(0xFFFFFFFFu, on ? (int)c.sh.xl[b][lane][1] : 0x7FFFFFFF);
+        r2 = __reduce_min_sync(0xFFFFFFFFu, on ? (int)c.sh.xl[b][lane][2] : 0x7FFFFFFF);
     }
     v0 = r0; v1 = r1; v2 = r2;
 }
@@ -573,7 +616,9 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
     u128 rs = g.s;
     unsigned long long rk = 0ull, pnext = g.has32 ? 1ull : 2ull;
     int i_cur = m - 1;
+    long long t0 = clock64();
     while (i_cur > SEQ_TAIL) {
+        ++c.n_rounds;
         const int L = i_cur - SEQ_TAIL;                      // accepts still wanted from the parallel part
         const unsigned long long kb = pnext >> 1;
         if (kb != rk) {
@@ -597,11 +642,17 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
             if (p0 + j >= pnext) validmask |= 1u << j;
         // fixed point of c_in = exclusive_prefix(accepts(c_in)); thread 0 is right from the start and
         // every sweep fixes at least one more thread (typically all of them within ~10 sweeps)
-        int c_in = 0, total = 0, a = local_accepts(raw, validmask, 0, i_cur, L), a_prev = -1;
+        // start from the expected accept count at the current acceptance rate (any start converges: the prefix of
+        // thread 0 is exact from the first exchange on, and every sweep fixes at least one more thread)
+        const uint32_t mask0 = 0xFFFFFFFFu >> __clz((uint32_t)i_cur);
+        const double rho = ((double)i_cur + 1.0) / ((double)mask0 + 1.0);
+        int c_in = min(L, (int)(rho * (double)(c.gtid * DPT))), total = 0, a_prev = -1;
+        int a = local_accepts(raw, validmask, c_in, i_cur, L);
         for (;;) {
             // one exchange per sweep: prefix of the accept counts + "did any count change since the last sweep";
             // when none changed the prefix is the one the counts were computed from, i.e. the fixed point
             bool any;
+            ++c.n_sweeps;
             const int c_new = c_scan_excl_any(c, a, total, a != a_prev, any);
             if (!any) break;
             a_prev = a;
@@ -649,16 +700,18 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
         }
         c.sh.i64[0] = (long long)t.s.hi;
         c.sh.i64[1] = (long long)t.s.lo;
-        c.sh.i32[2 * NW + 2] = (int)t.has32;
-        c.sh.i32[2 * NW + 3] = (int)t.buf32;
+        c.sh.i32[3 * NW + 2] = (int)t.has32;
+        c.sh.i32[3 * NW + 3] = (int)t.buf32;
     }
     __syncthreads();
     g.s.hi = (uint64_t)c.sh.i64[0];
     g.s.lo = (uint64_t)c.sh.i64[1];
-    g.has32 = (uint32_t)c.sh.i32[2 * NW + 2];
-    g.buf32 = (uint32_t)c.sh.i32[2 * NW + 3];
+    g.has32 = (uint32_t)c.sh.i32[3 * NW + 2];
+    g.buf32 = (uint32_t)c.sh.i32[3 * NW + 3];
     c.sync();
+    c.cy_resolve += clock64() - t0;
     if (!apply) return;
+    t0 = clock64();
 
     // ---- apply the swap sequence j[m-1..1] in parallel --------------------------------------
     for (int p = c.gtid; p < m; p += c.gth) w.cursor[p] = 0;
@@ -716,6 +769,7 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
         out[i] = cand ? cand[val] : val;
     }
     c.sync();
+    c.cy_apply += clock64() - t0;
 }
 
 __global__ void __launch_bounds__(GT) permutation_par_kernel(qa_pcg64* rng, int m, int32_t* out, ParWork w) {
@@ -1158,6 +1212,32 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[13] = (double)cy_load + 1e-9 * 0; state[14] = (double)cy_scan; state[15] = (double)cy_dec;
         state[16] = (double)cy_min; state[17] = (double)cy_commit; state[18] = (double)cy_gather;
         state[19] = (double)n_chunks; state[20] = (double)n_cutshort;
+        state[21] = (double)c.cy_resolve; state[22] = (double)c.cy_apply; state[23] = (double)c.n_sweeps + 65536.0 * c.n_rounds;
+    }
+}
+
+// micro-benchmark of the collectives (cycles per call), for DESIGN.md / tuning
+__global__ void __launch_bounds__(GT) collective_bench_kernel(double* out, int iters) {
+    __shared__ Sh sh;
+    Coop c(sh);
+    int v = threadIdx.x & 3, tot = 0;
+    bool any;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) v = c_scan_excl_any(c, v & 3, tot, (v & 1) != 0, any) & 7;
+    long long t1 = clock64();
+    int a = v, b = v + 1, d = v + 2;
+    for (int i = 0; i < iters; ++i) { c_min3(c, a, b, d); a += threadIdx.x & 1; }
+    long long t2 = clock64();
+    for (int i = 0; i < iters; ++i) c.sync();
+    long long t3 = clock64();
+    for (int i = 0; i < iters; ++i) __syncthreads();
+    long long t4 = clock64();
+    P2 tt[3] = {{v, v}, {1, 2}, {3, 3}}, pp[3];
+    for (int i = 0; i < iters; ++i) { scan_totals<3>(c, tt, pp); tt[0].d0 = pp[0].d0 & 3; }
+    long long t5 = clock64();
+    if (c.gtid == 0) {
+        out[0] = (double)(t1 - t0) / iters; out[1] = (double)(t2 - t1) / iters; out[2] = (double)(t3 - t2) / iters;
+        out[3] = (double)(t4 - t3) / iters; out[4] = (double)(t5 - t4) / iters; out[5] = (double)(a + tot + pp[1].d0);
     }
 }
 
@@ -1223,6 +1303,10 @@ static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args..
 }  // namespace qa
 
 using namespace qa;
+
+extern "C" int qa_collective_bench(double* out, int iters, int cluster, qa_stream_t stream) {
+    return launch_cluster(collective_bench_kernel, cluster, (cudaStream_t)stream, out, iters);
+}
 
 extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(32 * n) + al(n) + 512; }
 
