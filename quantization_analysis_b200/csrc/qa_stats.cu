@@ -121,7 +121,11 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     }
     const uint32_t E = __float_as_uint(mabs) >> 23;
     if (E == 0u) return;                         // every element is zero/denormal: flushed (x ~ 0)
-    if (E < 24u || E == 255u) {
+    // E < 72: squares of the group's elements fall into float32's denormal range, where the reference's float32
+    // products (x*x, y*y, x*y as float32 arrays) round or flush; E == 255: inf/nan.  Both take the generic path,
+    // which forms float32 products like the reference.  (An element below 2^-63 inside a group whose maximum is
+    // above 2^-55 still contributes its exact square here instead of a denormal-rounded one: < 2^-40 relative.)
+    if (E < 72u || E == 255u) {
         // rare: keep the caller's accumulators in registers by handing the slow path its own copy
         TileAcc t;
         acc_zero(t);

@@ -292,3 +292,43 @@ def test_striped_tables_concatenate_in_tile_order(qa):
     for a, b in sharding.row_stripes(x.shape[0], 3):
         parts.append(eng.tile_stats(eng.prepare_tiles(x[a:b]), G.MIXED))
     assert torch.equal(torch.cat(parts, dim=1), full)
+
+
+@pytest.mark.parametrize("kind", ["constant", "zeros", "one_tile", "mean_heavy", "tiny_values", "alternating_scale", "ragged"])
+def test_parallel_greedy_degenerate_inputs(qa, kind):
+    """Edge cases of the greedy: den == 0 branches, empty deltas, a non-zero mean (sum y is then a monotone sum
+    carried with the reference's rounding sequence), binade changes, ragged tiles.  Parallel == one-thread chain,
+    and both == the CPU oracle."""
+    eng = qa["engine"]
+    rng = np.random.default_rng(3)
+    if kind == "constant":
+        x = np.full((96, 128), 0.25, dtype=np.float32)
+    elif kind == "zeros":
+        x = np.zeros((64, 96), dtype=np.float32)
+    elif kind == "one_tile":
+        x = (rng.standard_normal((32, 32)) * 0.02).astype(np.float32)
+    elif kind == "mean_heavy":
+        x = (1.0 + rng.standard_normal((256, 384)) * 0.01).astype(np.float32)
+    elif kind == "tiny_values":
+        x = (rng.standard_normal((128, 256)) * 1e-30).astype(np.float32)
+    elif kind == "alternating_scale":
+        x = (rng.standard_normal((256, 256)) * 0.02).astype(np.float32)
+        x[::2] *= 1000.0
+    else:
+        x = (rng.standard_normal((130, 75)) * 0.02).astype(np.float32)
+    x = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    p = eng.prepare_tiles(x)
+    table_o = orc.tile_stat_table(x)
+    for metric, thr in (("pcc", 0.999), ("pcc", 0.9), ("mae", 1e-4)):
+        table = eng.tile_stats(p, G.MIXED, exact_abs=True)
+        a1, c1, s1 = eng.greedy_assign(table, p.numel, metric, thr, list(G.MIXED), eng.make_rng(5), parallel=False)
+        a2, c2, s2 = eng.greedy_assign(table, p.numel, metric, thr, list(G.MIXED), eng.make_rng(5), parallel=True)
+        assert torch.equal(a1, a2), (kind, metric, thr)
+        assert torch.equal(c1, c2)
+        want, counts = orc.greedy_assign(table_o, list(G.MIXED), metric, thr, 5)
+        assert np.array_equal(a2.cpu().numpy().reshape(want.shape), want), (kind, metric, thr)
+        assert {f: int(c2[i]) for i, f in enumerate(G.MIXED)} == counts
+        if kind == "mean_heavy" and metric == "pcc":
+            flags = int(s2.cpu().numpy()[6]) & 0xFFFF
+            assert flags == 0, flags                      # nothing degraded: all sums carried faithfully
+            assert np.array_equal(s1.cpu().numpy()[:5], s2.cpu().numpy()[:5])
