@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""Regenerate profiles/r1_summary.md from gpurun_out/ artefacts (bench JSON, ncu launch list, ncu raw page).
+Usage: python profiles/make_summary.py <tag>   (expects gpurun_out/bench_<tag>.json, launches_<tag>.csv, prof_<tag>.ncu-rep)"""
+import collections, csv, json, shutil, subprocess, sys
+tag = sys.argv[1]
+g = "gpurun_out/"
+subprocess.run(f"ncu -i {g}prof_{tag}.ncu-rep --page raw --csv > {g}{tag}_raw.csv 2>/dev/null", shell=True, check=True)
+rows = list(csv.reader(l for l in open(f"{g}launches_{tag}.csv") if not l.startswith("==")))
+hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[1:]:
+    if len(r) < len(hdr) or r[ix["Metric Name"]] != "gpu__time_duration.sum":
+        continue
+    name = r[ix["Kernel Name"]].split("(")[0]
+    v = float(r[ix["Metric Value"]].replace(",", "")); u = r[ix["Metric Unit"]]
+    us = v / 1e3 if u in ("ns", "nsecond") else v if u in ("us", "usecond") else v * 1e3
+    agg[name][0] += 1; agg[name][1] += us
+tot = sum(v[1] for v in agg.values())
+L = ["| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
+for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    L.append(f"| `{k}` | {n} | {us:.1f} | {us/n:.1f} | {100*us/tot:.2f}% |")
+rows = list(csv.reader(open(f"{g}{tag}_raw.csv")))
+hdr = rows[0]; units = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
+want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__cluster_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]
+K = []
+for r in rows[2:]:
+    d = {"kernel": r[ix["Kernel Name"]].split("(")[0]}
+    for w in want:
+        if w in ix:
+            d[w] = r[ix[w]] + " " + units[ix[w]]
+    K.append(d)
+b = json.loads(open(f"{g}bench_{tag}.json").read().strip().splitlines()[-1])
+md = ["# Round 1 - measured numbers of record (B200, sm_100a)", "",
+      "Regenerate with `python profiles/make_summary.py <tag>`; raw artefacts are committed beside this file.", "",
+      "## bench.py (cfg2: mixed-tile-greedy pcc>=0.999 over the five layer-0 self_attn shapes, 374 MB of bf16 per step)", "",
+      f"`python bench.py --steps {b['steps']} --warmup {b['warmup']}` on one B200 (SM clock {b['clocks']['sm_mhz']} MHz, throttle reasons {b['clocks']['reasons']}):", "",
+      f"* device-resident throughput (`value`): **{b['value']:.1f} GB/s** ({b['ms_per_step']:.3f} ms per step, {b['pct_of_8TBs']:.2f} % of 8 TB/s)",
+      f"* end to end from pinned host bf16 (`e2e`): **{b['e2e']['value']:.1f} GB/s** (H2D {b['e2e']['h2d_bytes_per_step']/1e6:.0f} MB per step: PCIe-bound)",
+      f"* CPU port of the reference algorithm on the box's host cores: **{b['cpu_baseline']['value']*1e3:.2f} MB/s** ({b['cpu_baseline']['cores']} processes, {b['cpu_baseline']['host_cpus']} host CPUs)",
+      "", "| kernel | ms/step (CUDA events) | algorithmic GB/s | fraction of the measured 6547 GB/s copy peak |", "|---|---:|---:|---:|"]
+for k in b["roofline_by_kernel"]:
+    md.append(f"| `{k['kernel']}` | {k['ms_per_step']:.3f} | {k['achieved_gbs']:.1f} | {k['frac']:.4f} |")
+md += ["", "Round-1 history of the same bench: one-thread greedy 0.87 GB/s (415 ms/step) -> block-parallel 27 GB/s -> thread-block",
+       "cluster with DSMEM exchange 141 GB/s -> no binade cuts from sum|x-y| / sum y 262 GB/s -> cheaper collectives 276 GB/s.",
+       "Stats kernel: 16 % -> 27 % (packed f32x2, xorsign clamp) -> 28 % (one CTA per 32x512 item).", "",
+       "## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`, same command; serialised and cold: compare shares)", ""] + L + ["",
+       "## ncu --set full, first captured launch per kernel (o_proj 7168x16384 = 117.4 M elements)", ""]
+for d in K:
+    md.append(f"### `{d['kernel']}`")
+    md += [f"* {w} = {d[w]}" for w in want if w in d]
+    md.append("")
+md += ["Reading.  `stats_fast_kernel`: DRAM traffic (235 MB read + 16 MB written before the kernel ends) equals the algorithmic bytes",
+       "(234.9 MB + 20.2 MB table): x is read exactly once.  26 instructions per element, issue slots ~65 % busy, FMA/ALU/XU(F2F)",
+       "pipes at 31/38/34 %: the kernel is instruction-bound (the FMA-pipe floor alone is ~70 us for this launch vs 36 us of HBM time).",
+       "`greedy_par_kernel`: one 16-CTA cluster, latency-bound (about 250 cluster-wide collectives of ~2k cycles and the L2 gathers of the",
+       "permutation); its DRAM traffic is the 20 MB table.  It is the critical path of the 5-tensor cfg2 step; with many tensors per GPU",
+       "(cfg5) the clusters of different tensors run side by side."]
+open("profiles/r1_summary.md", "w").write("\n".join(md) + "\n")
+for f in (f"bench_{tag}.json", f"launches_{tag}.csv", f"{tag}_raw.csv"):
+    shutil.copy(g + f, "profiles/" + f)
+print("\n".join(md[:16]))
