@@ -119,6 +119,17 @@ int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int 
                          qa_stream_t stream);
 int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* work,
                              qa_stream_t stream);
+/* The first two permutations of a greedy run (mixed_tile_greedy.py:228-231 for the base format and the first
+ * candidate format) depend only on the seed and the tile count.  qa_greedy_prefetch draws them ahead of time
+ * (e.g. on another stream while qa_tile_stats runs): pre_order int32[n] = visiting order of pass 2, *pre_rng =
+ * stream state after both.  qa_greedy_assign_par_pre consumes them (same results as qa_greedy_assign_par).
+ * `work` may be the greedy's own work buffer if the prefetch completes before the greedy starts. */
+int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int32_t* pre_order, qa_pcg64* pre_rng, void* work,
+                       qa_stream_t stream);
+int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric,
+                             double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
+                             int8_t* assignment, int64_t* counts, double* state, void* work,
+                             const int32_t* pre_order, const qa_pcg64* pre_rng, qa_stream_t stream);
 
 /* Diagnostic: cycles per call of the cluster collectives used by qa_greedy_assign_par
  * (out double[8] on device: scan+flag exchange, 3-way min, cluster.sync, __syncthreads, pair scan). */

@@ -25,6 +25,8 @@ class GreedyBatch:
         self.shapes = [tuple(int(v) for v in s) for s in shapes]
         n_streams = min(16, len(self.shapes)) if n_streams is None else n_streams     # one stream per tensor
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        self.prefetch = metric != "atol" and len(self.tile_formats) >= 2
         L = _lib.lib()
         self.slots = []
         rng0 = engine.make_rng(self.seed, self.device)
@@ -41,10 +43,13 @@ class GreedyBatch:
                 "work": torch.empty(max(L.qa_greedy_work_bytes(nt), L.qa_greedy_par_work_bytes(nt)), dtype=torch.uint8,
                                     device=self.device),
                 "rng": rng0.clone(),
+                "pre_order": torch.empty(nt, dtype=torch.int32, device=self.device),
+                "pre_rng": rng0.clone(),
             })
         self._rng0 = rng0
         self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
-        self.launches_per_step = (3 if metric == "atol" else 2) * len(self.slots)   # tile_stats + greedy (+ sums) per tensor
+        # tile_stats + greedy per tensor (+ assignment_sums for atol, + the permutation prefetch otherwise)
+        self.launches_per_step = 3 * len(self.slots)
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
@@ -56,20 +61,34 @@ class GreedyBatch:
         return sum(2 * s["numel"] for s in self.slots)
 
     # ---- compute -------------------------------------------------------------------------
-    def _enqueue(self, slot, stream, stats: bool = True, assign: bool = True) -> None:
+    def _enqueue(self, slot, stream, stats: bool = True, assign: bool = True, side=None) -> None:
         L = _lib.lib()
         sp = stream.cuda_stream
+        pre = assign and self.prefetch and side is not None
+        if pre:
+            # the first two permutations depend only on (seed, ntiles): draw them on a side stream while the
+            # tile-stat pass streams the tensor
+            side.wait_stream(stream)
+            check(L.qa_greedy_prefetch(self._rng0.data_ptr(), slot["ntiles"], slot["pre_order"].data_ptr(),
+                                       slot["pre_rng"].data_ptr(), slot["work"].data_ptr(), side.cuda_stream), "qa_greedy_prefetch")
         if stats:
             check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
                                   0xF, STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS,
                                   slot["table"].data_ptr(), sp), "qa_tile_stats")
         if assign:
             slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
-            fn = L.qa_greedy_assign if self.metric == "atol" else L.qa_greedy_assign_par
-            check(fn(slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
-                     METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
-                     slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
-                     slot["state"].data_ptr(), slot["work"].data_ptr(), sp), "qa_greedy_assign")
+            args = (slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
+                    METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
+                    slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
+                    slot["state"].data_ptr(), slot["work"].data_ptr())
+            if self.metric == "atol":
+                check(L.qa_greedy_assign(*args, sp), "qa_greedy_assign")
+            elif pre:
+                stream.wait_stream(side)
+                check(L.qa_greedy_assign_par_pre(*args, slot["pre_order"].data_ptr(), slot["pre_rng"].data_ptr(), sp),
+                      "qa_greedy_assign_par_pre")
+            else:
+                check(L.qa_greedy_assign_par(*args, sp), "qa_greedy_assign_par")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
                 check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
                                            slot["sums"].data_ptr(), sp), "qa_assignment_sums")
@@ -82,7 +101,7 @@ class GreedyBatch:
             st = self.streams[k % len(self.streams)]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                self._enqueue(self.slots[i], st, stats, assign)
+                self._enqueue(self.slots[i], st, stats, assign, side=self.side_streams[k % len(self.side_streams)])
         for st in self.streams:
             cur.wait_stream(st)
 
@@ -95,7 +114,7 @@ class GreedyBatch:
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
-                self._enqueue(self.slots[i], st)
+                self._enqueue(self.slots[i], st, side=self.side_streams[k % len(self.side_streams)])
         for st in self.streams:
             cur.wait_stream(st)
         return self.collect()

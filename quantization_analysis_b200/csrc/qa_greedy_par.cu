@@ -58,6 +58,8 @@ struct ParWork {
     int32_t* parent;  // [n]
     double* dbuf;     // [4][n]  per-candidate deltas in visiting order
     uint8_t* fixed;   // [n]
+    const int32_t* pre_order;   // optional: permutation #2 of n items, computed ahead by greedy_prefetch_kernel
+    const qa_pcg64* pre_rng;    //           and the stream state after permutations #1 and #2
 };
 
 struct P2 {          // increment of m if the incoming m is even / odd
@@ -782,6 +784,25 @@ __global__ void __launch_bounds__(GT) permutation_par_kernel(qa_pcg64* rng, int 
     if (c.gtid == 0) g.store(rng);
 }
 
+// The first two permutations of a greedy run do not depend on the data: the base pass permutes all n tiles (only the
+// stream position matters, the order is irrelevant) and, unless the base state already fails, the second pass permutes
+// all n tiles again.  This kernel computes both ahead of time so they can overlap the tile-stat pass on another stream.
+__global__ void __launch_bounds__(GT) greedy_prefetch_kernel(const qa_pcg64* rng_in, int n, int32_t* order_out,
+                                                             qa_pcg64* rng_out, ParWork w) {
+    __shared__ Sh sh;
+    Coop c(sh);
+    Pcg g;
+    g.load(rng_in);
+    c.sync();
+    permutation_par(c, g, n, nullptr, order_out, w, false);
+    permutation_par(c, g, n, nullptr, order_out, w, true);
+    if (c.gtid == 0) {
+        rng_out->inc_hi = g.inc.hi;
+        rng_out->inc_lo = g.inc.lo;
+        g.store(rng_out);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // faithful sequential sums of table columns (tile order): S_k = fl(S_{k-1} + t_k)
 // ---------------------------------------------------------------------------------------------
@@ -986,6 +1007,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     }
     consts_finish(k);
     unsigned chain_rounds = 0;
+    const int32_t* order_ptr = w.order;
     long long t_mark = clock64(), cyc_perm = 0, cyc_chain = 0;
     long long cy_load = 0, cy_scan = 0, cy_dec = 0, cy_min = 0, cy_commit = 0, cy_gather = 0, tq = 0;
     unsigned n_chunks = 0, n_cutshort = 0;
@@ -1006,11 +1028,24 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                 if (!w.fixed[t]) w.cand[run++] = t;
         }
         c.sync();
-        if (m == 0) break;
+        if (m == 0) {
+            // the base pass fixed every tile: only permutation #1 was consumed (rare; redo it if it was prefetched away)
+            if (fi == 1 && w.pre_order != nullptr && ord.n >= 2) permutation_par(c, g, nt, w.cand, w.order, w, false);
+            break;
+        }
         const bool base_pass = fi == 0;
         // ---- (2) visiting order ----------------------------------------------------------
         t_mark = clock64();
-        permutation_par(c, g, m, w.cand, w.order, w, !base_pass);
+        const bool have_pre = w.pre_order != nullptr && ord.n >= 2;
+        order_ptr = w.order;
+        if (have_pre && fi == 0) {
+            // permutations #1 and #2 were drawn ahead of time (greedy_prefetch_kernel); nothing to do for the base pass
+        } else if (have_pre && fi == 1) {
+            order_ptr = w.pre_order;          // m == nt here: candidates are 0..nt-1 in order, so perm[k] is the tile
+            g.load(w.pre_rng);
+        } else {
+            permutation_par(c, g, m, w.cand, w.order, w, !base_pass);
+        }
         cyc_perm += clock64() - t_mark;
         t_mark = clock64();
         if (base_pass) {
@@ -1029,7 +1064,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         tq = clock64();
         double drift = 0.0;                              // sum |delta sy| of the pass: how far sy can move
         for (int q = c.gtid; q < m; q += c.gth) {      // gather the deltas once, in visiting order
-            const int t = w.order[q];
+            const int t = order_ptr[q];
 #pragma unroll
             for (int s = 0; s < NS; ++s)
                 dq[s][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, S0 + s) * nt + t], table[(size_t)QA_STAT_FMT(prev, S0 + s) * nt + t]);
@@ -1148,7 +1183,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             double vals[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             double dabs = 0.0;
             for (int j = 0; j < cnt && lo + j < valid; ++j) {
-                const int t = w.order[pos + lo + j];
+                const int t = order_ptr[pos + lo + j];
                 if ((D >> j) & 1u) {
                     assignment[t] = (int8_t)fmt;
                     ++loc;
@@ -1257,6 +1292,8 @@ static ParWork carve(void* work, int64_t n) {
     w.parent = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.dbuf = reinterpret_cast<double*>(take(32 * n));
     w.fixed = reinterpret_cast<uint8_t*>(take(n));
+    w.pre_order = nullptr;
+    w.pre_rng = nullptr;
     return w;
 }
 
@@ -1316,9 +1353,35 @@ extern "C" int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_p
     return launch_cluster(permutation_par_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, out_perm, carve(work, n));
 }
 
+extern "C" int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int32_t* pre_order, qa_pcg64* pre_rng, void* work,
+                                  qa_stream_t stream) {
+    if (!rng || n <= 0 || n > 0x3FFFFFFF || !pre_order || !pre_rng || !work) { set_error("qa_greedy_prefetch: bad args"); return 1; }
+    return launch_cluster(greedy_prefetch_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, pre_order, pre_rng,
+                          carve(work, n));
+}
+
+static int greedy_par_launch(const double* table, int64_t ntiles, double numel, int metric, double threshold,
+                             const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment, int64_t* counts,
+                             double* state, void* work, const int32_t* pre_order, const qa_pcg64* pre_rng, qa_stream_t stream);
+
+extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
+                                        const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
+                                        int64_t* counts, double* state, void* work, const int32_t* pre_order,
+                                        const qa_pcg64* pre_rng, qa_stream_t stream) {
+    return greedy_par_launch(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state, work,
+                             pre_order, pre_rng, stream);
+}
+
 extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric, double threshold,
                                     const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
                                     int64_t* counts, double* state, void* work, qa_stream_t stream) {
+    return greedy_par_launch(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state, work,
+                             nullptr, nullptr, stream);
+}
+
+static int greedy_par_launch(const double* table, int64_t ntiles, double numel, int metric, double threshold,
+                             const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment, int64_t* counts,
+                             double* state, void* work, const int32_t* pre_order, const qa_pcg64* pre_rng, qa_stream_t stream) {
     if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !fmt_order || nfmt < 1 || nfmt > QA_NFMT || !rng || !assignment ||
         !counts || !state || !work) {
         set_error("qa_greedy_assign_par: bad args");
@@ -1330,9 +1393,11 @@ extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double 
     for (int i = 0; i < QA_NFMT; ++i) ord.fmt[i] = i < nfmt ? fmt_order[i] : 0;
     for (int i = 0; i < nfmt; ++i)
         if (ord.fmt[i] < 0 || ord.fmt[i] >= QA_NFMT) { set_error("qa_greedy_assign_par: bad format index"); return 1; }
+    ParWork pw = carve(work, ntiles);
+    if (pre_order && pre_rng) { pw.pre_order = pre_order; pw.pre_rng = pre_rng; }
     if (metric == QA_METRIC_PCC)
         return launch_cluster(greedy_par_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                              metric, threshold, ord, rng, assignment, counts, state, carve(work, ntiles));
+                              metric, threshold, ord, rng, assignment, counts, state, pw);
     return launch_cluster(greedy_par_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                          metric, threshold, ord, rng, assignment, counts, state, carve(work, ntiles));
+                          metric, threshold, ord, rng, assignment, counts, state, pw);
 }

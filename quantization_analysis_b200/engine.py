@@ -192,8 +192,21 @@ def numpy_integers(rng: torch.Tensor, k: int, n: int) -> torch.Tensor:
     return out
 
 
+def greedy_prefetch(rng: torch.Tensor, ntiles: int, work: torch.Tensor | None = None):
+    """Draw the two data-independent permutations of a greedy run ahead of time (qa_greedy_prefetch).
+    -> (pre_order int32[ntiles], pre_rng).  `rng` is not modified."""
+    L = _lib.lib()
+    dev = rng.device
+    pre_order = torch.empty(ntiles, dtype=torch.int32, device=dev)
+    pre_rng = torch.empty_like(rng)
+    if work is None:
+        work = torch.empty(L.qa_greedy_par_work_bytes(ntiles), dtype=torch.uint8, device=dev)
+    check(L.qa_greedy_prefetch(_ptr(rng), ntiles, _ptr(pre_order), _ptr(pre_rng), _ptr(work), _stream()), "qa_greedy_prefetch")
+    return pre_order, pre_rng
+
+
 def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor,
-                  parallel: bool | None = None):
+                  parallel: bool | None = None, prefetched=None):
     """-> (assignment int8[ntiles], counts int64[4], state float64[8]) on device.
     parallel=None: the block-parallel kernel for pcc / mae, the one-thread chain for atol."""
     nt = table.shape[1]
@@ -207,9 +220,10 @@ def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float
     order = _lib.int32_array([FMT_INDEX[f] for f in fmt_order])
     if parallel:
         work = torch.empty(L.qa_greedy_par_work_bytes(nt), dtype=torch.uint8, device=dev)
-        check(L.qa_greedy_assign_par(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),
-                                     _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work), _stream()),
-              "qa_greedy_assign_par")
+        pre_order, pre_rng = prefetched if prefetched is not None else (None, None)
+        check(L.qa_greedy_assign_par_pre(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order,
+                                         len(fmt_order), _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work),
+                                         _ptr(pre_order), _ptr(pre_rng), _stream()), "qa_greedy_assign_par")
     else:
         work = torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
         check(L.qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),

@@ -332,3 +332,21 @@ def test_parallel_greedy_degenerate_inputs(qa, kind):
             flags = int(s2.cpu().numpy()[6]) & 0xFFFF
             assert flags == 0, flags                      # nothing degraded: all sums carried faithfully
             assert np.array_equal(s1.cpu().numpy()[:5], s2.cpu().numpy()[:5])
+
+
+def test_greedy_prefetched_permutations_equal_inline(qa):
+    """qa_greedy_prefetch + qa_greedy_assign_par_pre give the same map, counts, state and stream position as the
+    kernel that draws its permutations inline - including the case where the base state already fails."""
+    eng = qa["engine"]
+    x = G.algo_input("het_256x512")
+    p = eng.prepare_tiles(x)
+    table = eng.tile_stats(p, G.MIXED, exact_abs=True)
+    for metric, thr, fmts in (("pcc", 0.995, list(G.MIXED)), ("mae", 3e-4, list(G.MIXED)), ("pcc", 0.9999, ["bfp4", "bfp2"]),
+                              ("pcc", 0.99, ["bfp8", "bfp4", "bfp2"])):
+        r1, r2 = eng.make_rng(31), eng.make_rng(31)
+        a1, c1, s1 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r1, parallel=True)
+        pre = eng.greedy_prefetch(r2, p.ntiles)
+        a2, c2, s2 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r2, parallel=True, prefetched=pre)
+        assert torch.equal(a1, a2) and torch.equal(c1, c2), (metric, thr, fmts)
+        assert torch.equal(r1, r2), (metric, thr, fmts)
+        assert torch.equal(s1[:8], s2[:8])
