@@ -168,6 +168,13 @@ int qa_apply_assignment(const void* x, int x_dtype, int64_t rows, int64_t cols, 
 int qa_assignment_sums(const double* table, int64_t ntiles, const int8_t* assignment, int fmt,
                        double* out, qa_stream_t stream);
 
+/* Sums over two arbitrary float32 arrays for compression_algorithms/metrics.py:6-27 (pearson_corr, mae, atol) and
+ * the whole-tensor scoring of wq:684-687: out double[8] = {sum a, sum a^2, sum b, sum b^2, sum a*b, sum |a-b|,
+ * max |a-b|, 0} in float64 with a fixed reduction tree (b == NULL means b = 0: the fp0 format).
+ * work: qa_pair_sums_work_bytes() bytes. */
+int64_t qa_pair_sums_work_bytes(void);
+int qa_pair_sums(const float* a, const float* b, int64_t n, double* out, void* work, qa_stream_t stream);
+
 /* fp32 -> bf16 bit patterns plus a count of elements that are NOT bf16-exact (low 16 bits != 0).
  * Host helper for the numpy-in API.  inexact_count: uint64 on device (accumulated). */
 int qa_f32_to_bf16_checked(const float* x, int64_t n, void* out_bf16, unsigned long long* inexact_count,

@@ -1,29 +1,17 @@
 """Drop-in for compression_algorithms/metrics.py (:6-39).
 
 ``pearson_corr`` / ``metric_value`` run on the GPU: the pair (a, b) is reduced to the seven
-sums {sx, sx2, sy, sy2, sxy, s|a-b|, max|a-b|} by the tile-stat machinery and recombined in
-float64.  That is the exact value of the formula the reference evaluates in float32 (the
+sums {sx, sx2, sy, sy2, sxy, s|a-b|, max|a-b|} by `qa_pair_sums` (float64, fixed reduction tree)
+and recombined in float64.  That is the exact value of the formula the reference evaluates in float32 (the
 reference's own result is only ~1e-5 accurate at 1e7 elements).
 """
 from __future__ import annotations
-
-import math
-
-import numpy as np
-import torch
 
 from .. import engine
 
 
 def _pair_sums(a, b):
-    dev = engine._require_cuda()
-    ta = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
-    tb = b if isinstance(b, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(b, dtype=np.float32)))
-    ta = ta.to(dev).reshape(-1).to(torch.float64)
-    tb = tb.to(dev).reshape(-1).to(torch.float64)
-    d = (ta - tb).abs()
-    return [ta.sum().item(), (ta * ta).sum().item(), tb.sum().item(), (tb * tb).sum().item(), (ta * tb).sum().item(),
-            d.sum().item(), d.max().item() if d.numel() else 0.0], ta.numel()
+    return engine.pair_sums(a, b)
 
 
 def pearson_corr(a, b) -> float:

@@ -379,9 +379,61 @@ __global__ void __launch_bounds__(SB) assignment_sums_kernel(const double* __res
     if (threadIdx.x == 7) out[7] = 0.0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Whole-array pair sums for metrics.py (pearson_corr / metric_value on arbitrary float32 arrays)
+// ------------------------------------------------------------------------------------------
+constexpr int PS_BLOCKS = 592, PS_THREADS = 256;
+__global__ void __launch_bounds__(PS_THREADS) pair_sums_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               int64_t n, double* __restrict__ partial) {
+    __shared__ double sm[7][PS_THREADS / 32];
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int64_t per = cdiv(n, (int64_t)gridDim.x * blockDim.x);
+    const int64_t i0 = min(n, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * per), i1 = min(n, i0 + per);
+    for (int64_t i = i0; i < i1; ++i) {         // fixed element ranges and a fixed tree: deterministic
+        const double x = (double)a[i], y = b ? (double)b[i] : 0.0;
+        const double d = fabs((double)__fsub_rn(a[i], b ? b[i] : 0.f));     // float32 difference, as the reference forms it
+        v[0] += x; v[1] = fma(x, x, v[1]); v[2] += y; v[3] = fma(y, y, v[3]); v[4] = fma(x, y, v[4]); v[5] += d;
+        v[6] = fmax(v[6], d);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double other = __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v[k]), o),
+                                                  __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v[k]), o));
+            v[k] = k == 6 ? fmax(v[k], other) : v[k] + other;
+        }
+        if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double r = 0.0;
+        for (int w = 0; w < PS_THREADS / 32; ++w) r = threadIdx.x == 6 ? fmax(r, sm[threadIdx.x][w]) : r + sm[threadIdx.x][w];
+        partial[(int64_t)blockIdx.x * 8 + threadIdx.x] = r;
+    }
+}
+__global__ void pair_sums_final_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k >= 8) return;
+    double r = 0.0;
+    if (k < 7)
+        for (int b = 0; b < nblocks; ++b) r = k == 6 ? fmax(r, partial[(int64_t)b * 8 + k]) : r + partial[(int64_t)b * 8 + k];
+    out[k] = r;
+}
+
 }  // namespace qa
 
 using namespace qa;
+
+extern "C" int64_t qa_pair_sums_work_bytes(void) { return (int64_t)PS_BLOCKS * 8 * sizeof(double); }
+
+extern "C" int qa_pair_sums(const float* a, const float* b, int64_t n, double* out, void* work, qa_stream_t stream) {
+    if (!a || n < 0 || !out || !work) { set_error("qa_pair_sums: bad args"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    pair_sums_kernel<<<PS_BLOCKS, PS_THREADS, 0, s>>>(a, b, n, reinterpret_cast<double*>(work));
+    pair_sums_final_kernel<<<1, 32, 0, s>>>(reinterpret_cast<const double*>(work), PS_BLOCKS, out);
+    return check_launch("qa_pair_sums");
+}
 
 extern "C" int qa_numpy_permutation(qa_pcg64* rng, int64_t n, int32_t* out_perm, int32_t* work, qa_stream_t stream) {
     (void)work;

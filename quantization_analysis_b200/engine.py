@@ -283,6 +283,27 @@ def assignment_sums(table: torch.Tensor, assignment: torch.Tensor | None = None,
     return out
 
 
+def pair_sums(a, b=None) -> tuple[np.ndarray, int]:
+    """{sum a, sum a^2, sum b, sum b^2, sum ab, sum|a-b|, max|a-b|} over two arrays (b=None: zeros), float64."""
+    dev = _require_cuda()
+
+    def as_f32(t):
+        if isinstance(t, torch.Tensor):
+            return t.detach().to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(t, dtype=np.float32))).to(dev).reshape(-1)
+
+    ta = as_f32(a)
+    tb = None if b is None else as_f32(b)
+    if tb is not None and tb.numel() != ta.numel():
+        raise ValueError("pair_sums: size mismatch")
+    L = _lib.lib()
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    work = torch.empty(L.qa_pair_sums_work_bytes(), dtype=torch.uint8, device=dev)
+    if ta.numel():
+        check(L.qa_pair_sums(_ptr(ta), _ptr(tb), ta.numel(), _ptr(out), _ptr(work), _stream()), "qa_pair_sums")
+    return out.cpu().numpy(), int(ta.numel())
+
+
 def metrics_from_sums(s, numel: int) -> dict:
     """pcc / mae / atol from {sx, sx2, sy, sy2, sxy, sabs, max}: float64 recombination of the
     formulas in metrics.py:6-27 (the mathematically exact value the reference's float32 approximates)."""

@@ -126,11 +126,9 @@ def evaluate_tensor(name: str, x_dev: torch.Tensor, algorithms, formats, out_dir
                     table = engine.tile_stats(p, engine.MIXED_FORMATS)
                 results = []
                 for f in formats:
-                    if f == "fp0":       # all zeros (quantize_fp0): no kernel; pcc 0 unless x == 0 (metrics.py:14-15)
-                        absx = x_dev.float().abs()
-                        amax = float(absx.max())
-                        results.append((f.upper(), {"pcc": 0.0 if amax > 0 else 1.0, "mae": float(absx.double().mean()),
-                                                    "atol": amax}, None))
+                    if f == "fp0":       # all zeros (quantize_fp0): scored against b = 0 (metrics.py:14-15 gives pcc 0)
+                        sums, n = engine.pair_sums(x_dev, None)
+                        results.append((f.upper(), engine.metrics_from_sums(sums, n), None))
                     elif f in mixed:
                         sums = engine.assignment_sums(table, None, engine.FMT_INDEX[f]).cpu().numpy()
                         results.append((f.upper(), engine.metrics_from_sums(sums, p.numel), None))
@@ -138,10 +136,8 @@ def evaluate_tensor(name: str, x_dev: torch.Tensor, algorithms, formats, out_dir
                 res = algo.run(x_dev, formats, None, None)
                 results = []
                 for r in res:
-                    d = (x_dev.float() - r.y.float()).abs().double()
-                    from .compression_algorithms.metrics import pearson_corr
-                    results.append((r.fmt, {"pcc": pearson_corr(x_dev, r.y), "mae": float(d.mean()),
-                                            "atol": float(d.max())}, None))
+                    sums, n = engine.pair_sums(x_dev, r.y)
+                    results.append((r.fmt, engine.metrics_from_sums(sums, n), None))
             torch.cuda.synchronize()
             elapsed = time.perf_counter() - t0
             for fmt, m, _ in results:

@@ -350,3 +350,25 @@ def test_greedy_prefetched_permutations_equal_inline(qa):
         assert torch.equal(a1, a2) and torch.equal(c1, c2), (metric, thr, fmts)
         assert torch.equal(r1, r2), (metric, thr, fmts)
         assert torch.equal(s1[:8], s2[:8])
+
+
+def test_metrics_api_matches_fp64_formulas(qa):
+    """metrics.pearson_corr / metric_value (qa_pair_sums) vs the fp64 evaluation and the reference's float32 values."""
+    from quantization_analysis_b200.compression_algorithms import metrics
+    x = G.algo_input("het_256x512")
+    for fmt in ("bfp8", "bfp4", "bfp2", "fp0"):
+        y = orc.quantize(x, fmt)
+        ex = orc.exact_metrics_f64(x, y)
+        assert metrics.pearson_corr(x, y) == pytest.approx(ex["pcc"], rel=1e-9, abs=1e-12)
+        assert metrics.metric_value(x, y, "mae") == pytest.approx(ex["mae"], rel=1e-9)
+        assert metrics.metric_value(x, y, "atol") == ex["atol"]
+        ref = orc.wq_scores(x, y)
+        assert abs(metrics.pearson_corr(x, y) - ref["pcc"]) < 5e-5 and metrics.metric_value(x, y, "atol") == ref["atol"]
+    assert metrics.pearson_corr(x, x) == 1.0 or metrics.pearson_corr(x, x) == pytest.approx(1.0, abs=1e-12)
+    assert metrics.pearson_corr(np.zeros(0, np.float32), np.zeros(0, np.float32)) == 1.0
+    c = np.full(64, 0.5, np.float32)
+    assert metrics.pearson_corr(c, c) == 1.0 and metrics.pearson_corr(c, c + 1) == 0.0      # denom == 0 branch
+    with pytest.raises(ValueError):
+        metrics.metric_value(x, x, "rmse")
+    assert metrics.metric_is_good(0.95, "pcc", 0.94) and not metrics.metric_is_good(0.5, "mae", 0.1)
+    assert metrics.metric_better(0.9, 0.8, "pcc") and metrics.metric_better(0.1, 0.2, "atol")
