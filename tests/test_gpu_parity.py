@@ -372,3 +372,57 @@ def test_metrics_api_matches_fp64_formulas(qa):
         metrics.metric_value(x, x, "rmse")
     assert metrics.metric_is_good(0.95, "pcc", 0.94) and not metrics.metric_is_good(0.5, "mae", 0.1)
     assert metrics.metric_better(0.9, 0.8, "pcc") and metrics.metric_better(0.1, 0.2, "atol")
+
+
+def test_fp32_inputs_take_the_general_path(qa):
+    """Non-bf16-exact float32 tensors (what a dequantised fp8 checkpoint looks like, hf_model_utils.py:209-215):
+    never truncated - strict NumPy-order stats, faithful tile scores, greedy / threshold maps all match the oracle."""
+    eng, ca = qa["engine"], qa["ca"]
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal((96, 200)) * 0.02).astype(np.float32)
+    x[5, 7] = 0.0
+    p = eng.prepare_tiles(x)
+    assert p.dtype_code == 1                                   # stayed float32
+    want = orc.tile_stat_table(x)
+    got = _table_from_device(eng.tile_stats(p, G.MIXED), None)  # strict is selected automatically
+    assert np.array_equal(got["sx"], want["sx"]) and np.array_equal(got["sx2"], want["sx2"])
+    for f in G.MIXED:
+        for k in ("sy", "sy2", "sxy", "sabs", "amax"):
+            assert np.array_equal(got[f][k], want[f][k]), (f, k)
+    s = eng.tile_scores(p, G.MIXED).cpu().numpy()
+    for mi, metric in enumerate(("pcc", "mae", "atol")):
+        sc = orc.padded_tile_scores(x, G.MIXED, metric)
+        for fi, f in enumerate(G.MIXED):
+            assert np.array_equal(s[mi, fi].view(np.uint32), sc[f].view(np.uint32)), (metric, f)
+    r = ca.create_algorithm("mixed-tile-greedy", {"metric": "pcc", "threshold": 0.995, "seed": 4}).run(x, G.FORMATS, None, None)[0]
+    a, counts = orc.greedy_assign(want, list(G.MIXED), "pcc", 0.995, 4)
+    assert np.array_equal(r.meta["assignment"], a) and r.tile_counts == counts
+    assert np.array_equal(G.bits(r.y), G.bits(orc.apply_assignment(x, a)))
+    t = ca.create_algorithm("mixed-tile-threshold", {"metric": "mae", "threshold": 3e-4}).run(x, G.FORMATS, None, None)[0]
+    sc = orc.padded_tile_scores(x, G.MIXED, "mae")
+    a2, c2 = orc.threshold_assign(sc, list(G.MIXED), "mae", 3e-4, want["th"], want["tw"])
+    assert np.array_equal(t.meta["assignment"], a2) and t.tile_counts == c2
+
+
+def test_random_bit_patterns_property(qa):
+    """Property test: random shapes (incl. ragged) filled with random bf16 / fp32 bit patterns (subnormals, inf, nan,
+    wide exponent spreads) - the device quantizers equal the oracle bit for bit."""
+    qf = qa["qf"]
+    rng = np.random.default_rng(2026)
+    for trial in range(40):
+        nd = int(rng.integers(1, 4))
+        shape = tuple(int(v) for v in rng.integers(1, 70, size=nd))
+        bits = rng.integers(0, 2**32, size=shape, dtype=np.uint64).astype(np.uint32)
+        mode = trial % 4
+        if mode == 0:
+            bits &= np.uint32(0xFFFF0000)                                   # arbitrary bf16 patterns
+        elif mode == 1:                                                     # narrow exponent band, bf16
+            e = rng.integers(100, 140, size=shape).astype(np.uint32)
+            bits = (bits & np.uint32(0x807F0000)) | (e << np.uint32(23))
+        elif mode == 2:                                                     # full fp32 mantissas, narrow band
+            e = rng.integers(110, 130, size=shape).astype(np.uint32)
+            bits = (bits & np.uint32(0x807FFFFF)) | (e << np.uint32(23))
+        x = bits.view(np.float32)
+        with np.errstate(all="ignore"):
+            for fmt in ("bf16", "bfp8", "bfp4", "bfp2"):
+                assert np.array_equal(G.bits(qf.quantize_weight_values(x, fmt)), G.bits(orc.quantize(x, fmt))), (trial, shape, fmt)
