@@ -71,6 +71,120 @@ struct OutPtrs {
     void* p[QA_NFMT];
 };
 
+// ---------------------------------------------------------------------------------------------
+// bf16 fast path.  In "group units" X = x * 2^(134-E) every reconstruction is a small dyadic number:
+// y = clamp(rne(X, step)) is (X + 1.5*2^23*step) - 1.5*2^23*step (ties to even, exact for bf16 inputs because no
+// significand bit is shifted out before the rounding) followed by min(|y|, (2^mb - 1)*step) with the sign of y;
+// scaling back by 2^(E-134) is exact and the upper 16 bits of the float32 pattern are the answer.
+// Groups with E < 24 (the trick's constants would leave float32's normal range), E == 0 or E == 255 (inf/nan) use
+// the integer recipe.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float clamp_sym(float y, float L) {
+    float r;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(r) : "f"(y), "f"(L));
+    return r;
+}
+__device__ __forceinline__ float max3abs(float m, float a, float b) {
+    float r;
+    asm("max.NaN.abs.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(a), "f"(b));   // a NaN must surface: its exponent is 255
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_hi16(float lo, float hi) {      // {bf16(lo), bf16(hi)} of exactly-representable values
+    return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+}
+__device__ __forceinline__ void fmt_consts(int fmt, float& M, float& L) {
+    M = fmt == 1 ? 25165824.f : fmt == 2 ? 402653184.f : 1610612736.f;     // 1.5 * 2^23 * step (2, 32, 128)
+    L = fmt == 1 ? 254.f : fmt == 2 ? 224.f : 128.f;                       // (2^mb - 1) * step
+}
+// one format of one group: w = 8 packed words in, out = 8 packed words
+__device__ __forceinline__ void group_recon_fast(const float2 (&X)[8], float M, float L, float back, uint32_t (&out)[8]) {
+    const float2 Mv = make_float2(M, M), nMv = make_float2(-M, -M), bv = make_float2(back, back);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float2 y = __fadd2_rn(__fadd2_rn(X[i], Mv), nMv);
+        y.x = clamp_sym(y.x, L);
+        y.y = clamp_sym(y.y, L);
+        y = __fmul2_rn(y, bv);
+        out[i] = pack_hi16(y.x, y.y);
+    }
+}
+// returns false when the group needs the integer recipe
+__device__ __forceinline__ bool group_prepare_fast(const uint32_t (&w)[8], float2 (&X)[8], float& back, uint32_t& E) {
+    float mabs = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        X[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xFFFF0000u));
+        mabs = max3abs(mabs, X[i].x, X[i].y);
+    }
+    E = __float_as_uint(mabs) >> 23;
+    if (E < 24u || E == 255u) return false;
+    const float inv = __uint_as_float((261u - E) << 23);   // 2^(134-E)
+    back = __uint_as_float((E - 7u) << 23);                 // 2^(E-134)
+    const float2 iv = make_float2(inv, inv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) X[i] = __fmul2_rn(X[i], iv);
+    return true;
+}
+__device__ __forceinline__ void group_recon_slow(const uint32_t (&w)[8], uint32_t E, int fmt, uint32_t (&out)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t lo = recon_bits(fmt, w[i] << 16, E), hi = recon_bits(fmt, w[i] & 0xFFFF0000u, E);
+        out[i] = (lo >> 16) | (hi & 0xFFFF0000u);
+    }
+}
+
+__global__ void __launch_bounds__(256) recon_fast_kernel(const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                                         int64_t gpr, uint32_t fmt_mask, OutPtrs out) {
+    const int64_t total = rows * gpr;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / gpr;
+        const int64_t col0 = (idx - row * gpr) * GROUP;
+        uint32_t w[8], y[8];
+        ldg256(x + row * ld + col0, w);
+        if (fmt_mask & 1u) stg256(reinterpret_cast<uint16_t*>(out.p[0]) + row * cols + col0, w);   // bf16 of bf16 = identity
+        float2 X[8];
+        float back;
+        uint32_t E;
+        const bool fast = group_prepare_fast(w, X, back, E);
+#pragma unroll
+        for (int f = 1; f < QA_NFMT; ++f) {
+            if (!((fmt_mask >> f) & 1u)) continue;
+            if (fast) {
+                float M, L;
+                fmt_consts(f, M, L);
+                group_recon_fast(X, M, L, back, y);
+            } else {
+                group_recon_slow(w, E, f, y);
+            }
+            stg256(reinterpret_cast<uint16_t*>(out.p[f]) + row * cols + col0, y);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) apply_fast_kernel(const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                                         int64_t gpr, int64_t tiles_w, const int8_t* __restrict__ assignment,
+                                                         uint16_t* __restrict__ out) {
+    const int64_t total = rows * gpr;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / gpr;
+        const int64_t g = idx - row * gpr;
+        const int fmt = assignment[(row / TILE) * tiles_w + (g >> 1)];
+        uint32_t w[8], y[8];
+        ldg256(x + row * ld + g * GROUP, w);
+        if (fmt >= 1) {                       // per-lane constants instead of per-format code: no divergence between tiles
+            float2 X[8];
+            float back, M, L;
+            uint32_t E;
+            fmt_consts(fmt, M, L);
+            if (group_prepare_fast(w, X, back, E)) group_recon_fast(X, M, L, back, y);
+            else group_recon_slow(w, E, fmt, y);
+            stg256(out + row * cols + g * GROUP, y);
+        } else {
+            stg256(out + row * cols + g * GROUP, w);
+        }
+    }
+}
+
 template <int DT, bool VEC>
 __global__ void __launch_bounds__(256) recon_kernel(const void* __restrict__ x, int64_t rows,
                                                     int64_t cols, int64_t ld, int64_t gpr,
@@ -180,7 +294,7 @@ extern "C" int qa_quant_recon(const void* x, int x_dtype, int64_t rows, int64_t 
     const int grid = grid_for(rows * gpr, 256);
     cudaStream_t s = (cudaStream_t)stream;
     if (x_dtype == QA_DT_BF16) {
-        if (vec) recon_kernel<QA_DT_BF16, true><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, fmt_mask, o);
+        if (vec) recon_fast_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(x), rows, cols, ld, gpr, fmt_mask, o);
         else recon_kernel<QA_DT_BF16, false><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, fmt_mask, o);
     } else {
         if (vec) recon_kernel<QA_DT_F32, true><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, fmt_mask, o);
@@ -200,7 +314,8 @@ extern "C" int qa_apply_assignment(const void* x, int x_dtype, int64_t rows, int
     const int grid = grid_for(rows * gpr, 256);
     cudaStream_t s = (cudaStream_t)stream;
     if (x_dtype == QA_DT_BF16) {
-        if (vec) apply_kernel<QA_DT_BF16, true><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, tiles_w, assignment, out_bf16);
+        if (vec) apply_fast_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint16_t*>(x), rows, cols, ld, gpr, tiles_w, assignment,
+                                                        reinterpret_cast<uint16_t*>(out_bf16));
         else apply_kernel<QA_DT_BF16, false><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, tiles_w, assignment, out_bf16);
     } else if (x_dtype == QA_DT_F32) {
         if (vec) apply_kernel<QA_DT_F32, true><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, tiles_w, assignment, out_bf16);

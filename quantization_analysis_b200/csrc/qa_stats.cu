@@ -79,7 +79,7 @@ __device__ __forceinline__ float clamp_sym(float y, float L) {
 }
 __device__ __forceinline__ float max3abs(float m, float a, float b) {
     float r;
-    asm("max.abs.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(a), "f"(b));
+    asm("max.NaN.abs.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(m), "f"(a), "f"(b));   // a NaN must surface: its exponent is 255
     return r;
 }
 
