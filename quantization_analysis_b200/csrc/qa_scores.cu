@@ -102,8 +102,21 @@ __global__ void __launch_bounds__(SC_WARPS * 32) tile_scores_kernel(
 #pragma unroll
             for (int i = 0; i < GROUP; ++i) u[i] = __float_as_uint(xs[r * SCP + c0 + i]);
             const uint32_t E = group_max_exp(u);
+            if (DT == QA_DT_BF16 && f >= 1 && E >= 24u && E != 255u) {
+                // bf16-exact values: magic-number rounding in group units (same arithmetic as recon_fast_kernel)
+                const float inv = __uint_as_float((261u - E) << 23), back = __uint_as_float((E - 7u) << 23);
+                const float M = f == 1 ? 25165824.f : f == 2 ? 402653184.f : 1610612736.f;
+                const float L = f == 1 ? 254.f : f == 2 ? 224.f : 128.f;
 #pragma unroll
-            for (int i = 0; i < GROUP; ++i) ys[r * SCP + c0 + i] = __uint_as_float(recon_bits(f, u[i], E));
+                for (int i = 0; i < GROUP; ++i) {
+                    float y = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(u[i]), inv), M), -M);
+                    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(y) : "f"(y), "f"(L));
+                    ys[r * SCP + c0 + i] = __fmul_rn(y, back);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < GROUP; ++i) ys[r * SCP + c0 + i] = __uint_as_float(recon_bits(f, u[i], E));
+            }
         }
         __syncwarp();
         const float mean_b = __fdiv_rn(pairwise1024([&](int r, int c) { return ys[r * SCP + c]; }, lane), 1024.f);
