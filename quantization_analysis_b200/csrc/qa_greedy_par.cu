@@ -85,6 +85,7 @@ struct Coop {
     int gtid, gth;       // cluster-wide thread id / thread count
     unsigned par;        // exchange counter (uniform): low bit = payload buffer and mbarrier phase parity
     long long cy_resolve = 0, cy_apply = 0; unsigned n_sweeps = 0, n_rounds = 0;   // diagnostics
+    long long cy_i0 = 0, cy_i1 = 0, cy_i2 = 0; unsigned n_init_rounds = 0;
     __device__ Coop(Sh& s) : sh(s), cl(cg::this_cluster()) {
         rank = cl.block_rank();
         nr = cl.num_blocks();
@@ -803,6 +804,12 @@ __global__ void __launch_bounds__(GT) greedy_prefetch_kernel(const qa_pcg64* rng
     }
 }
 
+// Per-thread staging of the chunk's addends in shared memory ([slot][thread] layout: conflict-free), so the
+// walks of a round read them at shared-memory latency instead of re-fetching from L2.
+constexpr int STAGE_SLOTS = 4 * EPS;                 // up to 4 streams x EPS elements per thread
+extern __shared__ double qa_stage[];
+__device__ __forceinline__ double& staged(int stream, int j) { return qa_stage[(stream * EPS + j) * GT + threadIdx.x]; }
+
 // ---------------------------------------------------------------------------------------------
 // faithful sequential sums of table columns (tile order): S_k = fl(S_{k-1} + t_k)
 // ---------------------------------------------------------------------------------------------
@@ -842,11 +849,17 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
     __syncthreads();
     const int CHc = c.gth * EPS;
     while (pos < nt) {
+        ++c.n_init_rounds;
         const int len = min(CHc, nt - pos);
         const int lo = c.gtid * EPS, hi = min(len, lo + EPS);          // this thread streams elements [lo, hi)
         Grid g[NC];
 #pragma unroll
         for (int s = 0; s < NC; ++s) g[s] = make_grid(S[s]);
+        static_assert(NC <= 4, "staging holds four streams");
+#pragma unroll
+        for (int s = 0; s < NC; ++s)
+#pragma unroll
+            for (int j = 0; j < EPS; ++j) staged(s, j) = lo + j < hi ? col[s][pos + lo + j] : 0.0;
         // walk 1: compose this thread's additions (stop at the first one that cannot ride the grid)
         P2 tot[NC], pre0[NC];
 #pragma unroll
@@ -858,7 +871,7 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
 #pragma unroll
             for (int s = 0; s < NC; ++s) {
                 p[s] = P2{0, 0};
-                if (!((degraded >> s) & 1u)) ok = classify(g[s], col[s][pos + idx], p[s]) && ok;
+                if (!((degraded >> s) & 1u)) ok = classify(g[s], staged(s, idx - lo), p[s]) && ok;
             }
             if (!ok) { bad = idx; break; }
 #pragma unroll
@@ -876,7 +889,7 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
                 for (int s = 0; s < NC; ++s) {
                     if ((degraded >> s) & 1u) continue;
                     P2 p{0, 0};
-                    classify(g[s], col[s][pos + idx], p);
+                    classify(g[s], staged(s, idx - lo), p);
                     run[s] = p2_then(run[s], p);
                     if (g[s].q != 0.0 && !in_binade(m_after(g[s], run[s]))) cut = min(cut, idx);
                 }
@@ -901,14 +914,14 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
                     for (int s = 0; s < NC; ++s) {
                         if ((degraded >> s) & 1u) continue;
                         P2 p{0, 0};
-                        classify(g[s], col[s][pos + idx], p);
+                        classify(g[s], staged(s, idx - lo), p);
                         run[s] = p2_then(run[s], p);
                     }
                 }
 #pragma unroll
                 for (int s = 0; s < NC; ++s) {
                     const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], run[s])) : S[s];
-                    vals[s] = __dadd_rn(before, col[s][pos + cut]);
+                    vals[s] = __dadd_rn(before, staged(s, cut - lo));
                 }
             }
             c_bcast_d(c, owner, vals, NC, nv);
@@ -976,7 +989,9 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                                            table + (size_t)QA_STAT_FMT(base, 2) * nt, table + (size_t)QA_STAT_FMT(base, 3) * nt};
             double R[4];
             unsigned dg;
+            const long long ti = clock64();
             faithful_init_sums<4>(c, cols, nt, R, dg, 1 << 30);
+            c.cy_i0 += clock64() - ti;
             k.sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
         }
         {   // signed sums (means).  A sum with heavy cancellation (|sum t| << sum |t|: zero-mean weights) is a
@@ -986,6 +1001,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             const double* const cols[2] = {table + (size_t)QA_STAT_SX * nt, table + (size_t)QA_STAT_FMT(base, 0) * nt};
             double R[2];
             bool walk[2];
+            const long long ti = clock64();
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 double sm = 0.0, sa = 0.0;
@@ -996,6 +1012,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             }
             if (walk[0] && walk[1]) degraded = 3u;
             else faithful_init_sums<2>(c, cols, nt, R, degraded, 24);
+            c.cy_i1 += clock64() - ti;
             k.sx = R[0]; S[0] = R[1];
         }
     } else {
@@ -1099,6 +1116,10 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             int valid = len;
             P2 pre0[NS];
             bool any_flag = guess;             // uniform: does any element of the chunk carry an accept flag?
+#pragma unroll
+            for (int s = 0; s < (PCC ? 4 : 1); ++s)
+#pragma unroll
+                for (int j = 0; j < EPS; ++j) staged(s, j) = j < cnt ? dq[PCC ? s : 0][pos + lo + j] : 0.0;
             cy_load += clock64() - tq;
             for (int round = 0; round < 64; ++round) {
                 ++chain_rounds;
@@ -1113,7 +1134,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                     P2 p[NS];
                     bool ok = true;
 #pragma unroll
-                    for (int s = 0; s < NS; ++s) ok = classify(gr[s], dq[s][pos + lo + j], p[s]) && ok;
+                    for (int s = 0; s < NS; ++s) ok = classify(gr[s], staged(s, j), p[s]) && ok;
                     if (!ok) { bad = lo + j; break; }
 #pragma unroll
                     for (int s = 0; s < NS; ++s) tot[s] = p2_then(tot[s], p[s]);
@@ -1136,11 +1157,11 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                         double cnd[4] = {0.0, 0.0, 0.0, 0.0}, dl[NS];
 #pragma unroll
                         for (int s = 0; s < NS; ++s) {
-                            dl[s] = dq[s][pos + idx];
+                            dl[s] = staged(s, j);
                             const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
                             cnd[S0 + s] = __dadd_rn(sb, dl[s]);
                         }
-                        if (PCC) cnd[3] = S[3] + dq[3][pos + idx];      // chunk-start value: only its zero test matters
+                        if (PCC) cnd[3] = S[3] + staged(3, j);          // chunk-start value: only its zero test matters
                         const bool dj = good_par(k, cnd);
                         const bool fj = (F >> j) & 1u;
                         D |= dj ? (1u << j) : 0u;
@@ -1187,7 +1208,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                 if ((D >> j) & 1u) {
                     assignment[t] = (int8_t)fmt;
                     ++loc;
-                    if (PCC) dabs += dq[3][pos + lo + j];
+                    if (PCC) dabs += staged(3, j);
                 } else w.fixed[t] = 1;
             }
             if (valid - 1 >= lo && valid - 1 < lo + EPS) {       // owner of the last committed element
@@ -1201,7 +1222,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
                         P2 p{0, 0};
-                        classify(gr[s], dq[s][pos + lo + j], p);
+                        classify(gr[s], staged(s, j), p);
                         run[s] = p2_then(run[s], p);
                     }
                 }
@@ -1209,7 +1230,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
-                    vals[S0 + s] = take ? __dadd_rn(sb, dq[s][pos + valid - 1]) : sb;
+                    vals[S0 + s] = take ? __dadd_rn(sb, staged(s, jl)) : sb;
                 }
                 vals[4] = take ? 1.0 : 0.0;
             }
@@ -1247,6 +1268,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[13] = (double)cy_load + 1e-9 * 0; state[14] = (double)cy_scan; state[15] = (double)cy_dec;
         state[16] = (double)cy_min; state[17] = (double)cy_commit; state[18] = (double)cy_gather;
         state[19] = (double)n_chunks; state[20] = (double)n_cutshort;
+        state[13] = (double)c.cy_i0; state[14] = (double)c.cy_i1; state[15] = (double)c.n_init_rounds;
         state[21] = (double)c.cy_resolve; state[22] = (double)c.cy_apply; state[23] = (double)c.n_sweeps + 65536.0 * c.n_rounds;
     }
 }
@@ -1313,10 +1335,12 @@ static int pick_cluster(int64_t n) {
 template <typename... KArgs, typename... Args>
 static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
     if (nr > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    constexpr int dyn = STAGE_SLOTS * GT * (int)sizeof(double);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nr, 1, 1);
     cfg.blockDim = dim3(GT, 1, 1);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = dyn;
     cfg.stream = s;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
