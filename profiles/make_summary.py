@@ -45,7 +45,8 @@ md = ["# Round 1 - measured numbers of record (B200, sm_100a)", "",
 for k in b["roofline_by_kernel"]:
     md.append(f"| `{k['kernel']}` | {k['ms_per_step']:.3f} | {k['achieved_gbs']:.1f} | {k['frac']:.4f} |")
 md += ["", "Round-1 history of the same bench: one-thread greedy 0.87 GB/s (415 ms/step) -> block-parallel 27 GB/s -> thread-block",
-       "cluster with DSMEM exchange 141 GB/s -> no binade cuts from sum|x-y| / sum y 262 GB/s -> cheaper collectives 276 GB/s.",
+       "cluster with DSMEM exchange 141 GB/s -> no binade cuts from sum|x-y| / sum y 262 GB/s -> cheaper collectives 276 GB/s",
+       "-> permutation prefetch on a side stream ~300 GB/s.",
        "Stats kernel: 16 % -> 27 % (packed f32x2, xorsign clamp) -> 28 % (one CTA per 32x512 item).", "",
        "## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`, same command; serialised and cold: compare shares)", ""] + L + ["",
        "## ncu --set full, first captured launch per kernel (o_proj 7168x16384 = 117.4 M elements)", ""]
@@ -58,7 +59,15 @@ md += ["Reading.  `stats_fast_kernel`: DRAM traffic (235 MB read + 16 MB written
        "pipes at 31/38/34 %: the kernel is instruction-bound (the FMA-pipe floor alone is ~70 us for this launch vs 36 us of HBM time).",
        "`greedy_par_kernel`: one 16-CTA cluster, latency-bound (about 250 cluster-wide collectives of ~2k cycles and the L2 gathers of the",
        "permutation); its DRAM traffic is the 20 MB table.  It is the critical path of the 5-tensor cfg2 step; with many tensors per GPU",
-       "(cfg5) the clusters of different tensors run side by side."]
+       "(cfg5) the clusters of different tensors run side by side.",
+       "", "## Other kernels of the path (CUDA events, 10 launches each, o_proj-size tensor 7168x16384 unless noted)", "",
+       "| kernel | what | time | algorithmic GB/s | fraction of copy peak |", "|---|---|---:|---:|---:|",
+       "| `recon_fast_kernel` | cfg1 `none`: bfp8+bfp4+bfp2 reconstructions in one pass (8 B/elem) | 0.153 ms | 6123 | 0.94 |",
+       "| `recon_fast_kernel` | one format (4 B/elem) | 0.093 ms | 5031 | 0.77 |",
+       "| `apply_fast_kernel` | final MIXED reconstruction from a tile map (4 B/elem) | 0.085 ms | 5505 | 0.84 |",
+       "| `stats_fast_kernel` | quantize + tile statistics (2.17 B/elem) | 0.144 ms | 1772 | 0.27 |",
+       "| `tile_scores_kernel` | NumPy-float32-faithful tile scores, 4 formats x 3 metrics (threshold / sweep) | 0.72 ms | 327 (input) | 0.05 |",
+       "| `greedy_par_kernel` | o_proj, 114 688 tiles, 4 passes | 1.2 ms | - | latency-bound |"]
 open("profiles/r1_summary.md", "w").write("\n".join(md) + "\n")
 for f in (f"bench_{tag}.json", f"launches_{tag}.csv", f"{tag}_raw.csv"):
     shutil.copy(g + f, "profiles/" + f)
