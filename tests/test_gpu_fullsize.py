@@ -108,3 +108,18 @@ def test_cfg5_expert_shapes_batch(env):
     table = eng.tile_stats(p, G.MIXED, exact_abs=False)
     a, _c, _s = eng.greedy_assign(table, p.numel, "pcc", 0.999, list(G.MIXED), eng.make_rng(123), parallel=False)
     assert np.array_equal(a.cpu().numpy().reshape(res[5]["assignment"].shape), res[5]["assignment"])
+
+
+def test_striped_greedy_over_nccl_two_gpus():
+    """(e) multi-GPU exchange step: needs >= 2 visible GPUs (skipped on a one-GPU box)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = Path(__file__).resolve().parent / "striped_greedy_worker.py"
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(worker)],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "striped_greedy_ok" in out.stdout
