@@ -119,17 +119,29 @@ int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int 
                          qa_stream_t stream);
 int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* work,
                              qa_stream_t stream);
-/* The first two permutations of a greedy run (mixed_tile_greedy.py:228-231 for the base format and the first
- * candidate format) depend only on the seed and the tile count.  qa_greedy_prefetch draws them ahead of time
- * (e.g. on another stream while qa_tile_stats runs): pre_order int32[n] = visiting order of pass 2, *pre_rng =
- * stream state after both.  qa_greedy_assign_par_pre consumes them (same results as qa_greedy_assign_par).
- * `work` may be the greedy's own work buffer if the prefetch completes before the greedy starts. */
-int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int32_t* pre_order, qa_pcg64* pre_rng, void* work,
-                       qa_stream_t stream);
+/* Staging of a greedy run, so that its three independent parts can overlap on different streams:
+ *
+ *  qa_greedy_prefetch  - the permutations that depend only on (seed, tile count): #1 for the base format (only its
+ *      stream position matters), #2 for the first candidate format, and - speculatively - #3 for the second one,
+ *      which is the permutation of all n tiles whenever pass 2 accepted every tile (mixed_tile_greedy.py:228-231).
+ *      pre_order int32[(nfmt >= 3 ? 2 : 1)][n] = visiting orders of passes 2 (and 3); pre_rng[same count] = stream
+ *      states after them.  The greedy checks the candidate count before it uses #3 and draws its own otherwise.
+ *      `work` (qa_greedy_par_work_bytes) may be the greedy's own buffer if the prefetch completes before it starts.
+ *  qa_greedy_init      - the data-dependent, permutation-independent part: the sequentially rounded initial sums
+ *      (mixed_tile_greedy.py:165-170) and the per-tile deltas of every format transition.  init: at least
+ *      qa_greedy_init_bytes(ntiles) bytes; fmt_order / metric must match the greedy call that consumes it.
+ *  qa_greedy_assign_par_pre - the accept/reject chain; pre_order / pre_rng and init may each be NULL (computed
+ *      inline).  Same results as qa_greedy_assign_par in every combination. */
+int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int nfmt, int32_t* pre_order, qa_pcg64* pre_rng,
+                       void* work, qa_stream_t stream);
+int64_t qa_greedy_init_bytes(int64_t ntiles);
+int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
+                   void* init, qa_stream_t stream);
 int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric,
                              double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
                              int8_t* assignment, int64_t* counts, double* state, void* work,
-                             const int32_t* pre_order, const qa_pcg64* pre_rng, qa_stream_t stream);
+                             const int32_t* pre_order, const qa_pcg64* pre_rng, const void* init,
+                             qa_stream_t stream);
 
 /* Diagnostic: cycles per call of the cluster collectives used by qa_greedy_assign_par
  * (out double[8] on device: scan+flag exchange, 3-way min, cluster.sync, __syncthreads, pair scan). */

@@ -43,13 +43,14 @@ class GreedyBatch:
                 "work": torch.empty(max(L.qa_greedy_work_bytes(nt), L.qa_greedy_par_work_bytes(nt)), dtype=torch.uint8,
                                     device=self.device),
                 "rng": rng0.clone(),
-                "pre_order": torch.empty(nt, dtype=torch.int32, device=self.device),
-                "pre_rng": rng0.clone(),
+                "pre_order": torch.empty((2, nt), dtype=torch.int32, device=self.device),
+                "pre_rng": torch.stack([rng0, rng0]).contiguous(),
+                "init": torch.empty(L.qa_greedy_init_bytes(nt), dtype=torch.uint8, device=self.device),
             })
         self._rng0 = rng0
         self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
-        # tile_stats + greedy per tensor (+ assignment_sums for atol, + the permutation prefetch otherwise)
-        self.launches_per_step = 3 * len(self.slots)
+        # atol: tile_stats + greedy + assignment_sums; pcc / mae: tile_stats + greedy_init + greedy (+ the permutation prefetch)
+        self.launches_per_step = (3 if metric == "atol" else 3 + int(self.prefetch)) * len(self.slots)
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
@@ -69,7 +70,7 @@ class GreedyBatch:
             # the first two permutations depend only on (seed, ntiles): draw them on a side stream while the
             # tile-stat pass streams the tensor
             side.wait_stream(stream)
-            check(L.qa_greedy_prefetch(self._rng0.data_ptr(), slot["ntiles"], slot["pre_order"].data_ptr(),
+            check(L.qa_greedy_prefetch(self._rng0.data_ptr(), slot["ntiles"], len(self.tile_formats), slot["pre_order"].data_ptr(),
                                        slot["pre_rng"].data_ptr(), slot["work"].data_ptr(), side.cuda_stream), "qa_greedy_prefetch")
         if stats:
             check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
@@ -83,12 +84,15 @@ class GreedyBatch:
                     slot["state"].data_ptr(), slot["work"].data_ptr())
             if self.metric == "atol":
                 check(L.qa_greedy_assign(*args, sp), "qa_greedy_assign")
-            elif pre:
-                stream.wait_stream(side)
-                check(L.qa_greedy_assign_par_pre(*args, slot["pre_order"].data_ptr(), slot["pre_rng"].data_ptr(), sp),
-                      "qa_greedy_assign_par_pre")
             else:
-                check(L.qa_greedy_assign_par(*args, sp), "qa_greedy_assign_par")
+                # initial sums + delta records on the main stream (overlaps the prefetch), then the chain
+                check(L.qa_greedy_init(slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order,
+                                       len(self.tile_formats), slot["init"].data_ptr(), sp), "qa_greedy_init")
+                if pre:
+                    stream.wait_stream(side)
+                check(L.qa_greedy_assign_par_pre(*args, slot["pre_order"].data_ptr() if pre else None,
+                                                 slot["pre_rng"].data_ptr() if pre else None, slot["init"].data_ptr(), sp),
+                      "qa_greedy_assign_par_pre")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
                 check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
                                            slot["sums"].data_ptr(), sp), "qa_assignment_sums")

@@ -56,11 +56,14 @@ struct ParWork {
     int32_t* bucket;  // [n]
     int32_t* succ;    // [n]
     int32_t* parent;  // [n]
-    double* dbuf;     // [4][n]  per-candidate deltas in visiting order
+    double* hdr;      // [32]    initial sums + diagnostics (greedy_init_kernel or the inline init phase)
+    double* delta;    // [3][n][4] per-tile deltas {sy, sy2, sxy, sabs} of the format transitions, tile order
     uint8_t* fixed;   // [n]
-    const int32_t* pre_order;   // optional: permutation #2 of n items, computed ahead by greedy_prefetch_kernel
-    const qa_pcg64* pre_rng;    //           and the stream state after permutations #1 and #2
+    const int32_t* pre_order;   // optional: permutations #2 (and #3) of n items, drawn ahead by greedy_prefetch_kernel
+    const qa_pcg64* pre_rng;    //           and the stream states after permutation #2 (and #3)
+    int npre;                   // how many permutations were drawn ahead (0, 2 or 3)
 };
+constexpr int HDR_DOUBLES = 32;
 
 struct P2 {          // increment of m if the incoming m is even / odd
     long long d0, d1;
@@ -603,13 +606,11 @@ __device__ __forceinline__ int local_accepts(const uint32_t (&raw)[DPT], uint32_
 // Generates numpy's permutation(m) from the stream in `g` (uniform: every thread of the cluster holds
 // the same copy) and writes out[k] = cand ? cand[perm[k]] : perm[k].  apply == false only advances
 // the stream (the visiting order is irrelevant when the running state cannot change).
-__device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int32_t* out, const ParWork& w, bool apply) {
+// Part 1 (perm_resolve): the swap targets j[m-1..1] and the stream position after them.
+// Part 2 (perm_apply):   the swap sequence applied to the identity, in parallel.
+__device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
     const int tid = threadIdx.x;
-    if (m <= 1) {
-        if (m == 1 && apply && c.gtid == 0) out[0] = cand ? cand[0] : 0;
-        c.sync();
-        return;
-    }
+    if (m <= 1) return;
     // jump constants: 4*gtid LCG steps (this thread's offset in a round) and one full round
     u128 am, ap, rm, rp;
     lcg_jump_consts(g.inc, 4ull * (uint64_t)c.gtid, am, ap);
@@ -713,10 +714,15 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
     g.buf32 = (uint32_t)c.sh.i32[3 * NW + 3];
     c.sync();
     c.cy_resolve += clock64() - t0;
-    if (!apply) return;
-    t0 = clock64();
+}
 
-    // ---- apply the swap sequence j[m-1..1] in parallel --------------------------------------
+__device__ void perm_apply(Coop& c, int m, const int32_t* cand, int32_t* out, const ParWork& w) {
+    if (m <= 1) {
+        if (m == 1 && c.gtid == 0) out[0] = cand ? cand[0] : 0;
+        c.sync();
+        return;
+    }
+    const long long t0 = clock64();
     for (int p = c.gtid; p < m; p += c.gth) w.cursor[p] = 0;
     c.sync();
     for (int i = 1 + c.gtid; i < m; i += c.gth) atomicAdd(&w.cursor[w.jarr[i]], 1);
@@ -775,6 +781,12 @@ __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int
     c.cy_apply += clock64() - t0;
 }
 
+__device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int32_t* out, const ParWork& w, bool apply) {
+    perm_resolve(c, g, m, w);
+    if (apply) perm_apply(c, m, cand, out, w);
+    else c.sync();
+}
+
 __global__ void __launch_bounds__(GT) permutation_par_kernel(qa_pcg64* rng, int m, int32_t* out, ParWork w) {
     __shared__ Sh sh;
     Coop c(sh);
@@ -785,22 +797,28 @@ __global__ void __launch_bounds__(GT) permutation_par_kernel(qa_pcg64* rng, int 
     if (c.gtid == 0) g.store(rng);
 }
 
-// The first two permutations of a greedy run do not depend on the data: the base pass permutes all n tiles (only the
-// stream position matters, the order is irrelevant) and, unless the base state already fails, the second pass permutes
-// all n tiles again.  This kernel computes both ahead of time so they can overlap the tile-stat pass on another stream.
-__global__ void __launch_bounds__(GT) greedy_prefetch_kernel(const qa_pcg64* rng_in, int n, int32_t* order_out,
+// The first permutations of a greedy run do not depend on the data: the base pass permutes all n tiles (only the
+// stream position matters, the order is irrelevant); unless the base state already fails, pass 2 permutes all n
+// tiles again; and when pass 2 accepts every tile (the usual outcome for the first, nearly lossless candidate
+// format) pass 3 permutes all n tiles once more.  This kernel draws them ahead of time so they overlap the
+// tile-stat pass on another stream; the greedy checks the candidate count before it uses the speculative third one.
+__global__ void __launch_bounds__(GT) greedy_prefetch_kernel(const qa_pcg64* rng_in, int n, int npre, int32_t* order_out,
                                                              qa_pcg64* rng_out, ParWork w) {
     __shared__ Sh sh;
     Coop c(sh);
     Pcg g;
     g.load(rng_in);
     c.sync();
-    permutation_par(c, g, n, nullptr, order_out, w, false);
-    permutation_par(c, g, n, nullptr, order_out, w, true);
-    if (c.gtid == 0) {
-        rng_out->inc_hi = g.inc.hi;
-        rng_out->inc_lo = g.inc.lo;
-        g.store(rng_out);
+    perm_resolve(c, g, n, w);                     // permutation #1: stream position only
+    for (int k = 0; k + 2 <= npre; ++k) {
+        c.sync();                                 // the previous apply has finished reading jarr
+        perm_resolve(c, g, n, w);
+        perm_apply(c, n, nullptr, order_out + (size_t)k * n, w);
+        if (c.gtid == 0) {
+            rng_out[k].inc_hi = g.inc.hi;
+            rng_out[k].inc_lo = g.inc.lo;
+            g.store(rng_out + k);
+        }
     }
 }
 
@@ -954,36 +972,18 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// the greedy kernel
+// init phase: initial sums + per-transition delta tables (data-dependent, permutation-independent)
 // ---------------------------------------------------------------------------------------------
+// hdr: [0] sx  [1] sx2  [2..5] sy, sy2, sxy, sabs of the base format  [6] degraded bits  [7] cycles
+//      [8] cycles of the non-negative columns  [9] cycles of the signed columns  [10] scan rounds
 template <bool PCC>
-__global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
-                                                        double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
-                                                        int64_t* counts, double* state, ParWork w) {
-    __shared__ Sh sh;
-    Coop c(sh);
-    const int tid = threadIdx.x;
+__device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, const ParOrder& ord, double* hdr, double* delta) {
     const int base = ord.fmt[0];
-    constexpr bool is_pcc = PCC;
-    // running sums carried with the reference's exact rounding sequence: sy, sy2, sxy (pcc) | sabs (mae).
-    // In pcc mode sum|x-y| only enters the degenerate den == 0 branch (mixed_tile_greedy.py:187-188): it is
-    // tracked as a plain per-chunk sum (it starts at 0 and would change binade ~40 times on its way up).
-    constexpr int NS = PCC ? 3 : 1;
-    constexpr int S0 = PCC ? 0 : 3;       // first table statistic among them
-    for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
-    if (tid < QA_NFMT) sh.cnt[tid] = 0;
-    if (c.gtid < QA_NFMT) counts[c.gtid] = c.gtid == base ? nt : 0;
-    Pcg g;
-    g.load(rng);
-    c.sync();
     const long long t_start = clock64();
-
-    // ---- (1) initial sums, sequentially rounded in tile order ------------------------------
-    Consts k;
-    k.n = numel; k.thr = thr; k.metric = metric; k.sx = 0.0; k.sx2 = 0.0;
+    double sx = 0.0, sx2 = 0.0;
     double S[4] = {0.0, 0.0, 0.0, 0.0};      // sy, sy2, sxy, sabs (mae uses S[3] only)
     unsigned degraded = 0;
-    if (is_pcc) {
+    if (PCC) {
         {   // sums of non-negative terms: few binade changes, always carried faithfully
             const double* const cols[4] = {table + (size_t)QA_STAT_SX2 * nt, table + (size_t)QA_STAT_FMT(base, 1) * nt,
                                            table + (size_t)QA_STAT_FMT(base, 2) * nt, table + (size_t)QA_STAT_FMT(base, 3) * nt};
@@ -992,7 +992,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             const long long ti = clock64();
             faithful_init_sums<4>(c, cols, nt, R, dg, 1 << 30);
             c.cy_i0 += clock64() - ti;
-            k.sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
+            sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
         }
         {   // signed sums (means).  A sum with heavy cancellation (|sum t| << sum |t|: zero-mean weights) is a
             // random walk that changes binade all the time; it goes straight to a fixed-order tree sum and is
@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             if (walk[0] && walk[1]) degraded = 3u;
             else faithful_init_sums<2>(c, cols, nt, R, degraded, 24);
             c.cy_i1 += clock64() - ti;
-            k.sx = R[0]; S[0] = R[1];
+            sx = R[0]; S[0] = R[1];
         }
     } else {
         const double* const cols[1] = {table + (size_t)QA_STAT_FMT(base, 3) * nt};
@@ -1022,13 +1022,78 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         faithful_init_sums<1>(c, cols, nt, R, dg, 1 << 30);
         S[3] = R[0];
     }
+    // delta[tr][t] = stats(fmt[tr+1]) - stats(fmt[tr]) of tile t: one 32-byte record per tile and transition, so the
+    // chain fetches a visited tile with one sector instead of eight
+    for (int tr = 0; tr + 1 < ord.n; ++tr) {
+        const int f0 = ord.fmt[tr], f1 = ord.fmt[tr + 1];
+        double2* dst = reinterpret_cast<double2*>(delta + (size_t)tr * nt * 4);
+        for (int t = c.gtid; t < nt; t += c.gth) {
+            double d[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                d[q] = __dsub_rn(table[(size_t)QA_STAT_FMT(f1, q) * nt + t], table[(size_t)QA_STAT_FMT(f0, q) * nt + t]);
+            dst[2 * (size_t)t] = make_double2(d[0], d[1]);
+            dst[2 * (size_t)t + 1] = make_double2(d[2], d[3]);
+        }
+    }
+    if (c.gtid == 0) {
+        hdr[0] = sx; hdr[1] = sx2; hdr[2] = S[0]; hdr[3] = S[1]; hdr[4] = S[2]; hdr[5] = S[3];
+        hdr[6] = (double)degraded;
+        hdr[7] = (double)(clock64() - t_start);
+        hdr[8] = (double)c.cy_i0; hdr[9] = (double)c.cy_i1; hdr[10] = (double)c.n_init_rounds;
+    }
+}
+
+template <bool PCC>
+__global__ void __launch_bounds__(GT) greedy_init_kernel(const double* __restrict__ table, int nt, ParOrder ord, double* hdr,
+                                                         double* delta) {
+    __shared__ Sh sh;
+    Coop c(sh);
+    init_phase<PCC>(c, table, nt, ord, hdr, delta);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the greedy kernel
+// ---------------------------------------------------------------------------------------------
+template <bool PCC>
+__global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
+                                                        double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
+                                                        int64_t* counts, double* state, ParWork w, int have_init) {
+    __shared__ Sh sh;
+    Coop c(sh);
+    const int tid = threadIdx.x;
+    const int base = ord.fmt[0];
+    constexpr bool is_pcc = PCC;
+    // running sums carried with the reference's exact rounding sequence: sy, sy2, sxy (pcc) | sabs (mae).
+    // In pcc mode sum|x-y| only enters the degenerate den == 0 branch (mixed_tile_greedy.py:187-188): it is
+    // tracked as a plain per-chunk sum (it starts at 0 and would change binade ~40 times on its way up).
+    constexpr int NS = PCC ? 3 : 1;
+    constexpr int S0 = PCC ? 0 : 3;       // first table statistic among them
+    for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
+    if (tid < QA_NFMT) sh.cnt[tid] = 0;
+    if (c.gtid < QA_NFMT) counts[c.gtid] = c.gtid == base ? nt : 0;
+    Pcg g;
+    g.load(rng);
+    c.sync();
+    const long long t_start = clock64();
+
+    // ---- (1) initial sums, sequentially rounded in tile order (greedy_init_kernel ran ahead, or inline) ----
+    if (!have_init) {
+        init_phase<PCC>(c, table, nt, ord, w.hdr, w.delta);
+        c.sync();
+    }
+    Consts k;
+    k.n = numel; k.thr = thr; k.metric = metric;
+    k.sx = w.hdr[0]; k.sx2 = w.hdr[1];
+    double S[4] = {w.hdr[2], w.hdr[3], w.hdr[4], w.hdr[5]};
+    unsigned degraded = (unsigned)w.hdr[6];
     consts_finish(k);
     unsigned chain_rounds = 0;
     const int32_t* order_ptr = w.order;
     long long t_mark = clock64(), cyc_perm = 0, cyc_chain = 0;
     long long cy_load = 0, cy_scan = 0, cy_dec = 0, cy_min = 0, cy_commit = 0, cy_gather = 0, tq = 0;
     unsigned n_chunks = 0, n_cutshort = 0;
-    const long long cyc_init = t_mark - t_start;
+    const long long cyc_init = have_init ? (long long)w.hdr[7] : t_mark - t_start;
     const int CHc = c.gth * EPS;
 
     for (int fi = 0; fi < ord.n; ++fi) {
@@ -1047,19 +1112,22 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         c.sync();
         if (m == 0) {
             // the base pass fixed every tile: only permutation #1 was consumed (rare; redo it if it was prefetched away)
-            if (fi == 1 && w.pre_order != nullptr && ord.n >= 2) permutation_par(c, g, nt, w.cand, w.order, w, false);
+            if (fi == 1 && w.pre_order != nullptr && w.npre >= 2 && ord.n >= 2) permutation_par(c, g, nt, w.cand, w.order, w, false);
             break;
         }
         const bool base_pass = fi == 0;
         // ---- (2) visiting order ----------------------------------------------------------
         t_mark = clock64();
-        const bool have_pre = w.pre_order != nullptr && ord.n >= 2;
+        const bool have_pre = w.pre_order != nullptr && w.npre >= 2 && ord.n >= 2;
         order_ptr = w.order;
         if (have_pre && fi == 0) {
             // permutations #1 and #2 were drawn ahead of time (greedy_prefetch_kernel); nothing to do for the base pass
         } else if (have_pre && fi == 1) {
             order_ptr = w.pre_order;          // m == nt here: candidates are 0..nt-1 in order, so perm[k] is the tile
             g.load(w.pre_rng);
+        } else if (have_pre && fi == 2 && w.npre >= 3 && m == nt) {
+            order_ptr = w.pre_order + nt;     // pass 2 accepted every tile: the speculative third permutation applies
+            g.load(w.pre_rng + 1);
         } else {
             permutation_par(c, g, m, w.cand, w.order, w, !base_pass);
         }
@@ -1077,24 +1145,15 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         // every candidate of pass fi was accepted in pass fi-1 (rejected tiles are fixed), so its
         // current format is the previous one in the order
         const int prev = ord.fmt[fi - 1];
-        double* dq[4] = {w.dbuf, w.dbuf + (size_t)nt, w.dbuf + 2 * (size_t)nt, w.dbuf + 3 * (size_t)nt};
+        const double* dtab = w.delta + (size_t)(fi - 1) * nt * 4;      // {d sy, d sy2, d sxy, d sabs} per tile
         tq = clock64();
-        double drift = 0.0;                              // sum |delta sy| of the pass: how far sy can move
-        for (int q = c.gtid; q < m; q += c.gth) {      // gather the deltas once, in visiting order
-            const int t = order_ptr[q];
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-                dq[s][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, S0 + s) * nt + t], table[(size_t)QA_STAT_FMT(prev, S0 + s) * nt + t]);
-            if (PCC) {
-                dq[3][q] = __dsub_rn(table[(size_t)QA_STAT_FMT(fmt, 3) * nt + t], table[(size_t)QA_STAT_FMT(prev, 3) * nt + t]);
-                drift += fabs(dq[0][q]);
-            }
-        }
-        c.sync();
         // sy is a signed sum near its mean: if the pass could carry it across a binade boundary (or zero),
         // run it on a fixed coarser grid instead of cutting a chunk at every hop
         bool relax_sy = false;
+        double drift = 0.0;                              // sum |delta sy| over the candidates: how far sy can move
         if (PCC) {
+            for (int t = c.gtid; t < nt; t += c.gth)
+                if (!w.fixed[t]) drift += fabs(dtab[4 * (size_t)t]);
             drift = c_reduce_d<false>(c, drift);
             relax_sy = !stays_in_binade(S[0], drift);
             if (relax_sy) degraded |= 4u;
@@ -1116,10 +1175,23 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             int valid = len;
             P2 pre0[NS];
             bool any_flag = guess;             // uniform: does any element of the chunk carry an accept flag?
+            {   // fetch the visited tiles' delta records (one 32-byte sector each)
+                double2 da[EPS], db[EPS];
 #pragma unroll
-            for (int s = 0; s < (PCC ? 4 : 1); ++s)
+                for (int j = 0; j < EPS; ++j) {
+                    da[j] = db[j] = make_double2(0.0, 0.0);
+                    if (j < cnt) {
+                        const double2* rec = reinterpret_cast<const double2*>(dtab) + 2 * (size_t)order_ptr[pos + lo + j];
+                        if (PCC) da[j] = rec[0];
+                        db[j] = rec[1];
+                    }
+                }
 #pragma unroll
-                for (int j = 0; j < EPS; ++j) staged(s, j) = j < cnt ? dq[PCC ? s : 0][pos + lo + j] : 0.0;
+                for (int j = 0; j < EPS; ++j) {
+                    if (PCC) { staged(0, j) = da[j].x; staged(1, j) = da[j].y; staged(2, j) = db[j].x; staged(3, j) = db[j].y; }
+                    else staged(0, j) = db[j].y;
+                }
+            }
             cy_load += clock64() - tq;
             for (int round = 0; round < 64; ++round) {
                 ++chain_rounds;
@@ -1266,9 +1338,9 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[11] = amax;
         state[12] = (double)c.nr;
         state[13] = (double)cy_load + 1e-9 * 0; state[14] = (double)cy_scan; state[15] = (double)cy_dec;
-        state[16] = (double)cy_min; state[17] = (double)cy_commit; state[18] = (double)cy_gather;
+        state[16] = (double)(clock64() - t_start); state[17] = (double)cy_commit; state[18] = (double)cy_gather;
         state[19] = (double)n_chunks; state[20] = (double)n_cutshort;
-        state[13] = (double)c.cy_i0; state[14] = (double)c.cy_i1; state[15] = (double)c.n_init_rounds;
+        state[13] = w.hdr[8]; state[14] = w.hdr[9]; state[15] = w.hdr[10];
         state[21] = (double)c.cy_resolve; state[22] = (double)c.cy_apply; state[23] = (double)c.n_sweeps + 65536.0 * c.n_rounds;
     }
 }
@@ -1312,10 +1384,12 @@ static ParWork carve(void* work, int64_t n) {
     w.bucket = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.succ = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.parent = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
-    w.dbuf = reinterpret_cast<double*>(take(32 * n));
     w.fixed = reinterpret_cast<uint8_t*>(take(n));
+    w.hdr = reinterpret_cast<double*>(take(8 * HDR_DOUBLES));
+    w.delta = reinterpret_cast<double*>(take(96 * n));
     w.pre_order = nullptr;
     w.pre_rng = nullptr;
+    w.npre = 0;
     return w;
 }
 
@@ -1369,7 +1443,9 @@ extern "C" int qa_collective_bench(double* out, int iters, int cluster, qa_strea
     return launch_cluster(collective_bench_kernel, cluster, (cudaStream_t)stream, out, iters);
 }
 
-extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(32 * n) + al(n) + 512; }
+extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(n) + al(8 * HDR_DOUBLES) + al(96 * n) + 512; }
+
+extern "C" int64_t qa_greedy_init_bytes(int64_t n) { return al(8 * HDR_DOUBLES) + al(96 * n) + 256; }
 
 extern "C" int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* work, qa_stream_t stream) {
     if (!rng || n < 0 || n > 0x3FFFFFFF || (n > 0 && (!out_perm || !work))) { set_error("qa_numpy_permutation_par: bad args"); return 1; }
@@ -1377,51 +1453,67 @@ extern "C" int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_p
     return launch_cluster(permutation_par_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, out_perm, carve(work, n));
 }
 
-extern "C" int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int32_t* pre_order, qa_pcg64* pre_rng, void* work,
+extern "C" int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int nfmt, int32_t* pre_order, qa_pcg64* pre_rng, void* work,
                                   qa_stream_t stream) {
-    if (!rng || n <= 0 || n > 0x3FFFFFFF || !pre_order || !pre_rng || !work) { set_error("qa_greedy_prefetch: bad args"); return 1; }
-    return launch_cluster(greedy_prefetch_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, pre_order, pre_rng,
-                          carve(work, n));
+    if (!rng || n <= 0 || n > 0x3FFFFFFF || nfmt < 2 || nfmt > QA_NFMT || !pre_order || !pre_rng || !work) {
+        set_error("qa_greedy_prefetch: bad args");
+        return 1;
+    }
+    return launch_cluster(greedy_prefetch_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, nfmt >= 3 ? 3 : 2, pre_order,
+                          pre_rng, carve(work, n));
 }
 
-static int greedy_par_launch(const double* table, int64_t ntiles, double numel, int metric, double threshold,
-                             const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment, int64_t* counts,
-                             double* state, void* work, const int32_t* pre_order, const qa_pcg64* pre_rng, qa_stream_t stream);
+static int fill_order(const int32_t* fmt_order, int nfmt, ParOrder& ord, const char* who) {
+    if (!fmt_order || nfmt < 1 || nfmt > QA_NFMT) { set_error("%s: bad format order", who); return 1; }
+    ord.n = nfmt;
+    for (int i = 0; i < QA_NFMT; ++i) ord.fmt[i] = i < nfmt ? fmt_order[i] : 0;
+    for (int i = 0; i < nfmt; ++i)
+        if (ord.fmt[i] < 0 || ord.fmt[i] >= QA_NFMT) { set_error("%s: bad format index", who); return 1; }
+    return 0;
+}
+
+extern "C" int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
+                              qa_stream_t stream) {
+    if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !init) { set_error("qa_greedy_init: bad args"); return 1; }
+    if (metric != QA_METRIC_PCC && metric != QA_METRIC_MAE) { set_error("qa_greedy_init: metric must be pcc or mae"); return 1; }
+    ParOrder ord;
+    if (fill_order(fmt_order, nfmt, ord, "qa_greedy_init")) return 1;
+    double* hdr = reinterpret_cast<double*>(init);
+    double* delta = reinterpret_cast<double*>(reinterpret_cast<char*>(init) + al(8 * HDR_DOUBLES));
+    if (metric == QA_METRIC_PCC)
+        return launch_cluster(greedy_init_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, ord, hdr, delta);
+    return launch_cluster(greedy_init_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, ord, hdr, delta);
+}
 
 extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
                                         const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
                                         int64_t* counts, double* state, void* work, const int32_t* pre_order,
-                                        const qa_pcg64* pre_rng, qa_stream_t stream) {
-    return greedy_par_launch(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state, work,
-                             pre_order, pre_rng, stream);
-}
-
-extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric, double threshold,
-                                    const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
-                                    int64_t* counts, double* state, void* work, qa_stream_t stream) {
-    return greedy_par_launch(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state, work,
-                             nullptr, nullptr, stream);
-}
-
-static int greedy_par_launch(const double* table, int64_t ntiles, double numel, int metric, double threshold,
-                             const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment, int64_t* counts,
-                             double* state, void* work, const int32_t* pre_order, const qa_pcg64* pre_rng, qa_stream_t stream) {
-    if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !fmt_order || nfmt < 1 || nfmt > QA_NFMT || !rng || !assignment ||
-        !counts || !state || !work) {
+                                        const qa_pcg64* pre_rng, const void* init, qa_stream_t stream) {
+    if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !rng || !assignment || !counts || !state || !work) {
         set_error("qa_greedy_assign_par: bad args");
         return 1;
     }
     if (metric != QA_METRIC_PCC && metric != QA_METRIC_MAE) { set_error("qa_greedy_assign_par: metric must be pcc or mae"); return 1; }
     ParOrder ord;
-    ord.n = nfmt;
-    for (int i = 0; i < QA_NFMT; ++i) ord.fmt[i] = i < nfmt ? fmt_order[i] : 0;
-    for (int i = 0; i < nfmt; ++i)
-        if (ord.fmt[i] < 0 || ord.fmt[i] >= QA_NFMT) { set_error("qa_greedy_assign_par: bad format index"); return 1; }
+    if (fill_order(fmt_order, nfmt, ord, "qa_greedy_assign_par")) return 1;
     ParWork pw = carve(work, ntiles);
-    if (pre_order && pre_rng) { pw.pre_order = pre_order; pw.pre_rng = pre_rng; }
+    if (pre_order && pre_rng && nfmt >= 2) { pw.pre_order = pre_order; pw.pre_rng = pre_rng; pw.npre = nfmt >= 3 ? 3 : 2; }
+    int have_init = 0;
+    if (init) {
+        pw.hdr = const_cast<double*>(reinterpret_cast<const double*>(init));
+        pw.delta = const_cast<double*>(reinterpret_cast<const double*>(reinterpret_cast<const char*>(init) + al(8 * HDR_DOUBLES)));
+        have_init = 1;
+    }
     if (metric == QA_METRIC_PCC)
         return launch_cluster(greedy_par_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                              metric, threshold, ord, rng, assignment, counts, state, pw);
+                              metric, threshold, ord, rng, assignment, counts, state, pw, have_init);
     return launch_cluster(greedy_par_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                          metric, threshold, ord, rng, assignment, counts, state, pw);
+                          metric, threshold, ord, rng, assignment, counts, state, pw, have_init);
+}
+
+extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric, double threshold,
+                                    const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
+                                    int64_t* counts, double* state, void* work, qa_stream_t stream) {
+    return qa_greedy_assign_par_pre(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state,
+                                    work, nullptr, nullptr, nullptr, stream);
 }

@@ -192,23 +192,35 @@ def numpy_integers(rng: torch.Tensor, k: int, n: int) -> torch.Tensor:
     return out
 
 
-def greedy_prefetch(rng: torch.Tensor, ntiles: int, work: torch.Tensor | None = None):
-    """Draw the two data-independent permutations of a greedy run ahead of time (qa_greedy_prefetch).
-    -> (pre_order int32[ntiles], pre_rng).  `rng` is not modified."""
+def greedy_prefetch(rng: torch.Tensor, ntiles: int, work: torch.Tensor | None = None, nfmt: int = NFMT):
+    """Draw the data-independent permutations of a greedy run ahead of time (qa_greedy_prefetch).
+    -> (pre_order int32[1 or 2][ntiles], pre_rng[1 or 2]).  `rng` is not modified."""
     L = _lib.lib()
     dev = rng.device
-    pre_order = torch.empty(ntiles, dtype=torch.int32, device=dev)
-    pre_rng = torch.empty_like(rng)
+    k = 2 if nfmt >= 3 else 1
+    pre_order = torch.empty((k, ntiles), dtype=torch.int32, device=dev)
+    pre_rng = torch.empty((k,) + tuple(rng.shape), dtype=rng.dtype, device=dev)
     if work is None:
         work = torch.empty(L.qa_greedy_par_work_bytes(ntiles), dtype=torch.uint8, device=dev)
-    check(L.qa_greedy_prefetch(_ptr(rng), ntiles, _ptr(pre_order), _ptr(pre_rng), _ptr(work), _stream()), "qa_greedy_prefetch")
+    check(L.qa_greedy_prefetch(_ptr(rng), ntiles, nfmt, _ptr(pre_order), _ptr(pre_rng), _ptr(work), _stream()), "qa_greedy_prefetch")
     return pre_order, pre_rng
 
 
+def greedy_init(table: torch.Tensor, metric: str, fmt_order) -> torch.Tensor:
+    """Initial sums + per-transition delta records of a greedy run (qa_greedy_init); consumed by greedy_assign(init=...)."""
+    L = _lib.lib()
+    nt = table.shape[1]
+    init = torch.empty(L.qa_greedy_init_bytes(nt), dtype=torch.uint8, device=table.device)
+    order = _lib.int32_array([FMT_INDEX[f] for f in fmt_order])
+    check(L.qa_greedy_init(_ptr(table), nt, METRIC_CODE[metric], order, len(fmt_order), _ptr(init), _stream()), "qa_greedy_init")
+    return init
+
+
 def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor,
-                  parallel: bool | None = None, prefetched=None):
-    """-> (assignment int8[ntiles], counts int64[4], state float64[8]) on device.
-    parallel=None: the block-parallel kernel for pcc / mae, the one-thread chain for atol."""
+                  parallel: bool | None = None, prefetched=None, init: torch.Tensor | None = None):
+    """-> (assignment int8[ntiles], counts int64[4], state float64[24]) on device.
+    parallel=None: the cluster-parallel kernel for pcc / mae, the one-thread chain for atol.
+    prefetched = greedy_prefetch(...) and init = greedy_init(...) are optional stages computed ahead of time."""
     nt = table.shape[1]
     dev = table.device
     L = _lib.lib()
@@ -221,9 +233,11 @@ def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float
     if parallel:
         work = torch.empty(L.qa_greedy_par_work_bytes(nt), dtype=torch.uint8, device=dev)
         pre_order, pre_rng = prefetched if prefetched is not None else (None, None)
+        if pre_order is not None and len(fmt_order) >= 3 and pre_order.shape[0] < 2:
+            raise ValueError("prefetched permutations were drawn for fewer formats than fmt_order has")
         check(L.qa_greedy_assign_par_pre(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order,
                                          len(fmt_order), _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work),
-                                         _ptr(pre_order), _ptr(pre_rng), _stream()), "qa_greedy_assign_par")
+                                         _ptr(pre_order), _ptr(pre_rng), _ptr(init), _stream()), "qa_greedy_assign_par")
     else:
         work = torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
         check(L.qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),

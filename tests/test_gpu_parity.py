@@ -334,22 +334,37 @@ def test_parallel_greedy_degenerate_inputs(qa, kind):
             assert np.array_equal(s1.cpu().numpy()[:5], s2.cpu().numpy()[:5])
 
 
-def test_greedy_prefetched_permutations_equal_inline(qa):
-    """qa_greedy_prefetch + qa_greedy_assign_par_pre give the same map, counts, state and stream position as the
-    kernel that draws its permutations inline - including the case where the base state already fails."""
+def test_greedy_staged_equals_inline(qa):
+    """qa_greedy_prefetch / qa_greedy_init + qa_greedy_assign_par_pre give the same map, counts, state and stream
+    position as the kernel that does everything inline, in every combination of stages - including a base state that
+    already fails, a pass 2 that accepts every tile (speculative third permutation used) and one that does not."""
     eng = qa["engine"]
     x = G.algo_input("het_256x512")
     p = eng.prepare_tiles(x)
     table = eng.tile_stats(p, G.MIXED, exact_abs=True)
+    seen_spec, seen_nospec = False, False
     for metric, thr, fmts in (("pcc", 0.995, list(G.MIXED)), ("mae", 3e-4, list(G.MIXED)), ("pcc", 0.9999, ["bfp4", "bfp2"]),
-                              ("pcc", 0.99, ["bfp8", "bfp4", "bfp2"])):
-        r1, r2 = eng.make_rng(31), eng.make_rng(31)
+                              ("pcc", 0.99, ["bfp8", "bfp4", "bfp2"]), ("pcc", 0.99999, list(G.MIXED)),
+                              ("mae", 1e-5, list(G.MIXED)), ("pcc", 0.9, ["bfp2", "bfp4", "bfp8"])):
+        r1 = eng.make_rng(31)
         a1, c1, s1 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r1, parallel=True)
-        pre = eng.greedy_prefetch(r2, p.ntiles)
-        a2, c2, s2 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r2, parallel=True, prefetched=pre)
-        assert torch.equal(a1, a2) and torch.equal(c1, c2), (metric, thr, fmts)
-        assert torch.equal(r1, r2), (metric, thr, fmts)
-        assert torch.equal(s1[:8], s2[:8])
+        if len(fmts) >= 3:
+            if int(c1[eng.FMT_INDEX[fmts[0]]]) == 0:
+                seen_spec = True
+            elif int(c1[eng.FMT_INDEX[fmts[0]]]) < p.ntiles:
+                seen_nospec = True
+        for use_pre in (False, True):
+            for use_init in (False, True):
+                if not (use_pre or use_init):
+                    continue
+                r2 = eng.make_rng(31)
+                pre = eng.greedy_prefetch(r2, p.ntiles, nfmt=len(fmts)) if use_pre else None
+                init = eng.greedy_init(table, metric, fmts) if use_init else None
+                a2, c2, s2 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r2, parallel=True, prefetched=pre, init=init)
+                assert torch.equal(a1, a2) and torch.equal(c1, c2), (metric, thr, fmts, use_pre, use_init)
+                assert torch.equal(r1, r2), (metric, thr, fmts, use_pre, use_init)
+                assert torch.equal(s1[:8], s2[:8])
+    assert seen_spec and seen_nospec
 
 
 def test_metrics_api_matches_fp64_formulas(qa):
