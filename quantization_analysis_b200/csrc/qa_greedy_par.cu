@@ -71,7 +71,7 @@ struct P2 {          // increment of m if the incoming m is even / odd
 
 struct Sh {
     int i32[3 * NW + 8];
-    long long i64[NW * 6 * 2 + 16];
+    long long i64[NW * 4 * 2 * 2 + 16];
     double f64[16];
     // cluster exchange (double buffered; written by remote CTAs through DSMEM)
     int xi[2][MAXR];
@@ -114,11 +114,6 @@ struct Coop {
     // scope), and every thread waits until all nr CTAs have arrived on the local one (acquire).  About an
     // order of magnitude cheaper than barrier.cluster with 16 x 512 threads.
     __device__ __forceinline__ void xarrive_wait() {
-#ifdef QA_XCHG_CLUSTER_SYNC
-        cl.sync();
-        ++par;
-        return;
-#endif
         const uint32_t local = (uint32_t)__cvta_generic_to_shared(&sh.mbar);
         if (threadIdx.x < nr) {
             uint32_t remote;
@@ -317,6 +312,7 @@ __device__ __forceinline__ P2 p2_then(P2 a, P2 b) {   // apply a, then b
 struct Grid {        // binade of the running sum at the start of a chunk
     double q;        // ulp (power of two); 0 => no grid (S == 0, inf/nan or denormal range)
     double invq;
+    double sinvq;    // sign / q: maps an addend to signed grid units
     long long m0;    // |S| / q, in [2^52, 2^53)   (relaxed: S / q, signed, |m0| < 2^52)
     double sign;     // +1 / -1
     bool relaxed;    // fixed coarser grid that cannot be left: accurate (<= 1 ulp of the bound) but not the
@@ -326,10 +322,11 @@ __device__ __forceinline__ Grid make_grid(double S) {
     Grid g;
     const int e = (int)((__double2hiint(S) >> 20) & 0x7FF);
     g.relaxed = false;
-    if (e < 64 || e > 1900) { g.q = 0.0; g.invq = 0.0; g.m0 = 0; g.sign = 1.0; return g; }
+    if (e < 64 || e > 1900) { g.q = 0.0; g.invq = 0.0; g.sinvq = 0.0; g.m0 = 0; g.sign = 1.0; return g; }
     g.q = __hiloint2double((e - 52) << 20, 0);
     g.invq = __hiloint2double((1023 + 1023 + 52 - e) << 20, 0);
     g.sign = S < 0.0 ? -1.0 : 1.0;
+    g.sinvq = g.sign * g.invq;
     g.m0 = __double2ll_rn(fabs(S) * g.invq);
     return g;
 }
@@ -341,9 +338,10 @@ __device__ __forceinline__ Grid make_grid_relaxed(double S, double bound) {
     if (e < 64) e = 64;
     g.relaxed = true;
     g.sign = 1.0;
-    if (e > 1900) { g.q = 0.0; g.invq = 0.0; g.m0 = 0; return g; }
+    if (e > 1900) { g.q = 0.0; g.invq = 0.0; g.sinvq = 0.0; g.m0 = 0; return g; }
     g.q = __hiloint2double((e - 52) << 20, 0);
     g.invq = __hiloint2double((1023 + 1023 + 52 - e) << 20, 0);
+    g.sinvq = g.invq;
     g.m0 = __double2ll_rn(S * g.invq);
     return g;
 }
@@ -357,7 +355,17 @@ __device__ __forceinline__ bool stays_in_binade(double S, double bound) {
 __device__ __forceinline__ bool classify(const Grid& g, double t, P2& out) {
     if (t == 0.0) { out = P2{0, 0}; return true; }      // adding zero never moves the sum
     if (g.q == 0.0) return false;
-    const double v = (t * g.sign) * g.invq;             // exact scaling by a power of two
+    const double v = t * g.sinvq;                       // exact scaling by a power of two
+    if (fabs(v) < 2251799813685248.0) {                 // |v| < 2^51: round to nearest-even integer with the 1.5 * 2^52 trick
+        const double M = 6755399441055744.0;
+        const double r = __dadd_rn(v, M);               // ulp(r) == 1, M even: r - M = v rounded to nearest, ties to even
+        const long long rn = __double_as_longlong(r) - __double_as_longlong(M);
+        const double fr = __dsub_rn(v, __dsub_rn(r, M));   // exact, in [-1/2, 1/2]
+        out.d0 = rn;                                    // incoming m even: the tie goes to the even increment
+        out.d1 = rn;
+        if (fabs(fr) == 0.5) out.d1 = rn + (fr > 0.0 ? 1ll : -1ll);   // incoming m odd: to the odd increment
+        return true;
+    }
     if (!(fabs(v) < 4.0e18)) return false;
     const double fl = floor(v);
     const long long a = __double2ll_rd(v);
@@ -369,8 +377,12 @@ __device__ __forceinline__ bool classify(const Grid& g, double t, P2& out) {
     return true;
 }
 __device__ __forceinline__ long long m_after(const Grid& g, P2 p) { return g.m0 + ((g.m0 & 1ll) ? p.d1 : p.d0); }
-__device__ __forceinline__ double s_of(const Grid& g, long long m) { return g.sign * ((double)m * g.q); }
 __device__ __forceinline__ bool in_binade(long long m) { return m >= M_LO && m < M_HI; }
+__device__ __forceinline__ double s_of(const Grid& g, long long m) {
+    // m in [2^52, 2^53) is its own float64 mantissa: exponent field 1075, no int -> float conversion needed
+    const double md = in_binade(m) ? __longlong_as_double(m + (1074ll << 52)) : (double)m;
+    return g.sign * (md * g.q);
+}
 __device__ __forceinline__ bool left_grid(const Grid& g, long long m) { return g.q != 0.0 && !g.relaxed && !in_binade(m); }
 
 __device__ __forceinline__ P2 shfl_up_p2(P2 v, int o) {
@@ -390,94 +402,109 @@ __device__ __forceinline__ long long lanes_incl_scan64(long long x) {
     return x;
 }
 
+__device__ __forceinline__ P2 lanes_incl_scan_p2(P2 v, int width) {       // inclusive pair scan over lanes [0, width)
+    const int lane = threadIdx.x & 31;
+    for (int o = 1; o < width; o <<= 1) {
+        const P2 y = shfl_up_p2(v, o);
+        if (lane >= o) v = p2_then(y, v);
+    }
+    return v;
+}
+
 // Exclusive cluster-wide scan (cluster thread order) of one P2 per stream per thread.
-// Exact ties are rare (the addend must end exactly half an ulp of the running sum): a CTA whose elements are all
-// tie-free has state-independent increments (d0 == d1) and scans plain int64 sums; only a CTA that saw a tie runs
-// the pair scan.  CTA totals are exchanged as pairs either way and composed in rank order.
+//  level 1  every warp scans its 32 thread totals.  Exact ties (an addend that ends exactly half an ulp of the
+//           running sum) make the increment depend on the parity of the incoming state; a warp without one has
+//           d0 == d1 everywhere and scans plain int64 sums instead of pairs.
+//  level 2  warp s (s < NS) scans the NW warp totals of stream s and sends the CTA total to every CTA of the cluster.
+//  level 3  after the exchange, warp s scans the CTA totals and publishes, per warp, the prefix of everything before it.
+// Levels 2 and 3 run on NS warps only (one stream each) while the others wait at the closing barrier: the redundant
+// per-warp copies of those scans used to cost more issue slots than the walks they serve.
 template <int NS>
 __device__ __forceinline__ void scan_totals(Coop& c, const P2 (&tot)[NS], P2 (&pre)[NS]) {
     Sh& sh = c.sh;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    static_assert(NS <= 4 && NS <= NW, "one warp per stream");
+    long long* wt = sh.i64;                       // [NW][NS][2] warp totals
+    long long* wp = sh.i64 + NW * 4 * 2;          // [NW][NS][2] prefix of everything before warp w (cluster-wide)
     bool tie = false;
 #pragma unroll
     for (int s = 0; s < NS; ++s) tie = tie || (tot[s].d0 != tot[s].d1);
-    P2 ctot[NS];
-    if (!__syncthreads_or(tie ? 1 : 0)) {
-        long long inc[NS];
+    P2 inc[NS];
+    if (!__any_sync(0xFFFFFFFFu, tie)) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            inc[s] = lanes_incl_scan64(tot[s].d0);
-            if (lane == 31) sh.i64[w * NS + s] = inc[s];
+            const long long v = lanes_incl_scan64(tot[s].d0);
+            inc[s] = P2{v, v};
         }
-        __syncthreads();
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const long long wt = lanes_incl_scan64(lane < NW ? sh.i64[lane * NS + s] : 0ll);
-            const long long all = __shfl_sync(0xFFFFFFFFu, wt, NW - 1);
-            const long long before = __shfl_sync(0xFFFFFFFFu, wt, (w + 31) & 31);
-            const long long v = (w ? before : 0ll) + inc[s] - tot[s].d0;
-            pre[s] = P2{v, v};
-            ctot[s] = P2{all, all};
-        }
-        __syncthreads();
     } else {
-        P2 inc[NS];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            inc[s] = tot[s];
+        for (int s = 0; s < NS; ++s) inc[s] = lanes_incl_scan_p2(tot[s], 32);
+    }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const P2 y = shfl_up_p2(inc[s], o);
-                if (lane >= o) inc[s] = p2_then(y, inc[s]);
-            }
-            if (lane == 31) { sh.i64[(w * NS + s) * 2] = inc[s].d0; sh.i64[(w * NS + s) * 2 + 1] = inc[s].d1; }
-        }
-        __syncthreads();
+    for (int s = 0; s < NS; ++s)
+        if (lane == 31) { wt[(w * NS + s) * 2] = inc[s].d0; wt[(w * NS + s) * 2 + 1] = inc[s].d1; }
+    P2 lanes_before[NS];
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            P2 t{0, 0};
-            if (lane < NW) { t.d0 = sh.i64[(lane * NS + s) * 2]; t.d1 = sh.i64[(lane * NS + s) * 2 + 1]; }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const P2 y = shfl_up_p2(t, o);
-                if (lane >= o) t = p2_then(y, t);
-            }
-            P2 before, all;
-            before.d0 = __shfl_sync(0xFFFFFFFFu, t.d0, (w + 31) & 31);
-            before.d1 = __shfl_sync(0xFFFFFFFFu, t.d1, (w + 31) & 31);
+    for (int s = 0; s < NS; ++s) {
+        lanes_before[s] = shfl_up_p2(inc[s], 1);
+        if (lane == 0) lanes_before[s] = P2{0, 0};
+    }
+    __syncthreads();
+    const unsigned b = c.par & 1u;
+    if (w < NS) {
+        const int s = w;
+        P2 t{0, 0};
+        if (lane < NW) { t.d0 = wt[(lane * NS + s) * 2]; t.d1 = wt[(lane * NS + s) * 2 + 1]; }
+        t = lanes_incl_scan_p2(t, NW);
+        P2 before = shfl_up_p2(t, 1);             // everything in this CTA before warp `lane`
+        if (lane == 0) before = P2{0, 0};
+        P2 cp{0, 0};                              // everything in the cluster before this CTA
+        if (c.nr > 1) {
+            P2 all;
             all.d0 = __shfl_sync(0xFFFFFFFFu, t.d0, NW - 1);
             all.d1 = __shfl_sync(0xFFFFFFFFu, t.d1, NW - 1);
-            if (w == 0) before = P2{0, 0};
-            P2 lanes_before = shfl_up_p2(inc[s], 1);
-            if (lane == 0) lanes_before = P2{0, 0};
-            pre[s] = p2_then(before, lanes_before);
-            ctot[s] = all;
-        }
-        __syncthreads();
-    }
-    if (c.nr > 1) {
-        const unsigned b = c.par & 1u;
-        if (threadIdx.x < c.nr) {
-            long long* dst = c.cl.map_shared_rank(&sh.xl[b][c.rank][0], threadIdx.x);
-#pragma unroll
-            for (int s = 0; s < NS; ++s) { dst[2 * s] = ctot[s].d0; dst[2 * s + 1] = ctot[s].d1; }
-        }
-        c.xarrive_wait();
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            P2 t{0, 0};
-            if (lane < (int)c.nr) { t.d0 = sh.xl[b][lane][2 * s]; t.d1 = sh.xl[b][lane][2 * s + 1]; }
-#pragma unroll
-            for (int o = 1; o < MAXR; o <<= 1) {
-                const P2 y = shfl_up_p2(t, o);
-                if (lane >= o) t = p2_then(y, t);
+            if (lane < (int)c.nr) {
+                long long* dst = c.cl.map_shared_rank(&sh.xl[b][c.rank][0], lane);
+                dst[2 * s] = all.d0;
+                dst[2 * s + 1] = all.d1;
             }
-            P2 cp;
-            cp.d0 = __shfl_sync(0xFFFFFFFFu, t.d0, (c.rank + 31) & 31);
-            cp.d1 = __shfl_sync(0xFFFFFFFFu, t.d1, (c.rank + 31) & 31);
+            // the NS payload warps meet, then warp 0 signals every CTA; all NS warps wait for the cluster's arrivals
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * NS) : "memory");
+            const uint32_t local = (uint32_t)__cvta_generic_to_shared(&sh.mbar);
+            if (threadIdx.x < c.nr) {
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(threadIdx.x));
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+            }
+            const uint32_t parity = c.par & 1u;
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(local), "r"(parity)
+                    : "memory");
+            }
+            P2 u{0, 0};
+            if (lane < (int)c.nr) { u.d0 = sh.xl[b][lane][2 * s]; u.d1 = sh.xl[b][lane][2 * s + 1]; }
+            u = lanes_incl_scan_p2(u, MAXR);
+            cp.d0 = __shfl_sync(0xFFFFFFFFu, u.d0, (c.rank + 31) & 31);
+            cp.d1 = __shfl_sync(0xFFFFFFFFu, u.d1, (c.rank + 31) & 31);
             if (c.rank == 0) cp = P2{0, 0};
-            pre[s] = p2_then(cp, pre[s]);
         }
+        const P2 pw = p2_then(cp, before);
+        if (lane < NW) { wp[(lane * NS + s) * 2] = pw.d0; wp[(lane * NS + s) * 2 + 1] = pw.d1; }
+    }
+    ++c.par;                                      // one exchange, counted by every thread
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        P2 pw;
+        pw.d0 = wp[(w * NS + s) * 2];
+        pw.d1 = wp[(w * NS + s) * 2 + 1];
+        pre[s] = p2_then(pw, lanes_before[s]);
     }
 }
 
@@ -868,8 +895,19 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
     const int CHc = c.gth * EPS;
     while (pos < nt) {
         ++c.n_init_rounds;
-        const int len = min(CHc, nt - pos);
-        const int lo = c.gtid * EPS, hi = min(len, lo + EPS);          // this thread streams elements [lo, hi)
+        // chunk length: a round ends at the first binade crossing anyway, so do not walk far past the point where
+        // the fastest-growing column is expected to reach its next power of two (addends ~ S / pos each)
+        double want = (double)CHc;
+#pragma unroll
+        for (int s = 0; s < NC; ++s) {
+            const double a = fabs(S[s]);
+            if (((degraded >> s) & 1u) || !(a > 0.0) || !(a < 1e300)) continue;
+            const double top = __hiloint2double((__double2hiint(a) & 0x7FF00000) + 0x00100000, 0);   // next power of two
+            want = fmin(want, (top - a) / a * (double)pos * 1.15 + 64.0);
+        }
+        const int len = min(max((int)want, c.gth), min(CHc, nt - pos));
+        const int per = (len + c.gth - 1) / c.gth;                      // 1..EPS elements per thread
+        const int lo = c.gtid * per, hi = min(len, lo + per);          // this thread streams elements [lo, hi)
         Grid g[NC];
 #pragma unroll
         for (int s = 0; s < NC; ++s) g[s] = make_grid(S[s]);
@@ -919,7 +957,7 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
         // state after element `cut` = fl(S_before(cut) + t_cut): a real add from the exact state before it
         double nv[NC];
         {
-            const bool owner = cut >= lo && cut < lo + EPS;
+            const bool owner = cut >= lo && cut < lo + per;
             double vals[NC];
 #pragma unroll
             for (int s = 0; s < NC; ++s) vals[s] = 0.0;
