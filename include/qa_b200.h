@@ -132,6 +132,16 @@ int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* 
  *      qa_greedy_init_bytes(ntiles) bytes; fmt_order / metric must match the greedy call that consumes it.
  *  qa_greedy_assign_par_pre - the accept/reject chain; pre_order / pre_rng and init may each be NULL (computed
  *      inline).  Same results as qa_greedy_assign_par in every combination. */
+/* The two halves of one numpy permutation, for callers that pipeline them across streams (a resolve needs the
+ * stream state of the previous one; an apply only needs its own swap targets):
+ *  qa_perm_resolve - swap targets jarr int32[n] (entries 1..n-1; NULL = only advance the stream) and the stream state
+ *      after the permutation (rng_out may alias rng_in).  One cluster.
+ *  qa_perm_apply   - out[k] = cand ? cand[perm[k]] : perm[k] from the swap targets, as grid kernels on the whole GPU.
+ *      work: at least qa_perm_apply_work_bytes(n) bytes. */
+int qa_perm_resolve(const qa_pcg64* rng_in, int64_t n, int32_t* jarr, qa_pcg64* rng_out, qa_stream_t stream);
+int64_t qa_perm_apply_work_bytes(int64_t n);
+int qa_perm_apply(const int32_t* jarr, int64_t n, const int32_t* cand, int32_t* out, void* work,
+                  qa_stream_t stream);
 int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int nfmt, int32_t* pre_order, qa_pcg64* pre_rng,
                        void* work, qa_stream_t stream);
 int64_t qa_greedy_init_bytes(int64_t ntiles);

@@ -26,6 +26,7 @@ class GreedyBatch:
         n_streams = min(16, len(self.shapes)) if n_streams is None else n_streams     # one stream per tensor
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
         self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        self.side2_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
         self.prefetch = metric != "atol" and len(self.tile_formats) >= 2
         L = _lib.lib()
         self.slots = []
@@ -46,11 +47,23 @@ class GreedyBatch:
                 "pre_order": torch.empty((2, nt), dtype=torch.int32, device=self.device),
                 "pre_rng": torch.stack([rng0, rng0]).contiguous(),
                 "init": torch.empty(L.qa_greedy_init_bytes(nt), dtype=torch.uint8, device=self.device),
+                "jarr": torch.empty((2, nt), dtype=torch.int32, device=self.device),
+                "rng1": rng0.clone(),
+                "apply_work": torch.empty((2, L.qa_perm_apply_work_bytes(nt)), dtype=torch.uint8, device=self.device),
+                "ev": torch.cuda.Event(),
             })
         self._rng0 = rng0
+        self._graphs = {}
         self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
-        # atol: tile_stats + greedy + assignment_sums; pcc / mae: tile_stats + greedy_init + greedy (+ the permutation prefetch)
-        self.launches_per_step = (3 if metric == "atol" else 3 + int(self.prefetch)) * len(self.slots)
+        # kernels of ours per tensor and step.  atol: tile_stats + greedy + assignment_sums.  pcc / mae: tile_stats +
+        # greedy_init + greedy chain, plus the prefetched permutations (a resolve kernel each, 7 grid kernels per apply)
+        if metric == "atol":
+            per_tensor = 3
+        elif not self.prefetch:
+            per_tensor = 3
+        else:
+            per_tensor = 3 + (3 + 2 * 7 if len(self.tile_formats) >= 3 else 2 + 7)
+        self.launches_per_step = per_tensor * len(self.slots)
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
@@ -67,11 +80,28 @@ class GreedyBatch:
         sp = stream.cuda_stream
         pre = assign and self.prefetch and side is not None
         if pre:
-            # the first two permutations depend only on (seed, ntiles): draw them on a side stream while the
-            # tile-stat pass streams the tensor
+            # the first permutations depend only on (seed, ntiles): draw them on side streams while the tile-stat pass
+            # streams the tensor.  Resolves chain through the RNG state (#1 -> #2 -> #3, one cluster each); each apply
+            # only needs its own swap targets and runs as grid kernels, #2's on a second side stream next to resolve #3.
+            side, side2 = side
+            n, three = slot["ntiles"], len(self.tile_formats) >= 3
             side.wait_stream(stream)
-            check(L.qa_greedy_prefetch(self._rng0.data_ptr(), slot["ntiles"], len(self.tile_formats), slot["pre_order"].data_ptr(),
-                                       slot["pre_rng"].data_ptr(), slot["work"].data_ptr(), side.cuda_stream), "qa_greedy_prefetch")
+            sa = side.cuda_stream
+            check(L.qa_perm_resolve(self._rng0.data_ptr(), n, None, slot["rng1"].data_ptr(), sa), "qa_perm_resolve")
+            check(L.qa_perm_resolve(slot["rng1"].data_ptr(), n, slot["jarr"][0].data_ptr(), slot["pre_rng"][0].data_ptr(), sa),
+                  "qa_perm_resolve")
+            if three:
+                slot["ev"].record(side)
+                side2.wait_event(slot["ev"])
+                check(L.qa_perm_apply(slot["jarr"][0].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
+                                      slot["apply_work"][0].data_ptr(), side2.cuda_stream), "qa_perm_apply")
+                check(L.qa_perm_resolve(slot["pre_rng"][0].data_ptr(), n, slot["jarr"][1].data_ptr(), slot["pre_rng"][1].data_ptr(), sa),
+                      "qa_perm_resolve")
+                check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][1].data_ptr(),
+                                      slot["apply_work"][1].data_ptr(), sa), "qa_perm_apply")
+            else:
+                check(L.qa_perm_apply(slot["jarr"][0].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
+                                      slot["apply_work"][0].data_ptr(), sa), "qa_perm_apply")
         if stats:
             check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
                                   0xF, STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS,
@@ -90,6 +120,8 @@ class GreedyBatch:
                                        len(self.tile_formats), slot["init"].data_ptr(), sp), "qa_greedy_init")
                 if pre:
                     stream.wait_stream(side)
+                    if len(self.tile_formats) >= 3:
+                        stream.wait_stream(side2)
                 check(L.qa_greedy_assign_par_pre(*args, slot["pre_order"].data_ptr() if pre else None,
                                                  slot["pre_rng"].data_ptr() if pre else None, slot["init"].data_ptr(), sp),
                       "qa_greedy_assign_par_pre")
@@ -105,9 +137,25 @@ class GreedyBatch:
             st = self.streams[k % len(self.streams)]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                self._enqueue(self.slots[i], st, stats, assign, side=self.side_streams[k % len(self.side_streams)])
+                self._enqueue(self.slots[i], st, stats, assign, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
         for st in self.streams:
             cur.wait_stream(st)
+
+    def capture(self, stats: bool = True, assign: bool = True) -> None:
+        """Record one pass (all tensors, all streams) into a CUDA graph; ``run_graph`` replays it with one launch.
+        The pass is ~25 small launches per tensor, so eager enqueueing costs about as much host time as the GPU
+        needs to run it; the inputs are the resident ``slot['x']`` buffers, so replays see whatever was loaded last."""
+        self.run(stats, assign)                       # eager once: module load, kernel attributes, allocator warm-up
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run(stats, assign)
+        self._graphs[(stats, assign)] = g
+
+    def run_graph(self, stats: bool = True, assign: bool = True) -> None:
+        if (stats, assign) not in self._graphs:
+            self.capture(stats, assign)
+        self._graphs[(stats, assign)].replay()
 
     def run_from_host(self, host_tensors) -> list[dict]:
         """End-to-end pass: pinned host bf16 -> device, quantize+score+assign, results back to host."""
@@ -118,7 +166,7 @@ class GreedyBatch:
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
-                self._enqueue(self.slots[i], st, side=self.side_streams[k % len(self.side_streams)])
+                self._enqueue(self.slots[i], st, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
         for st in self.streams:
             cur.wait_stream(st)
         return self.collect()

@@ -26,6 +26,7 @@
 //    steps that last wrote the position it reads.
 #include <cooperative_groups.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "qa_common.cuh"
@@ -106,8 +107,8 @@ struct Coop {
     }
     // full cluster barrier (global-memory phases): orders global writes and invalidates L1
     __device__ __forceinline__ void sync() {
-        if (nr == 1) __syncthreads();
-        else cl.sync();
+        __syncthreads();                 // every thread's writes happen-before the arrivals below (cumulativity)
+        if (nr > 1) xarrive_wait();      // release / acquire at cluster scope; ~10x cheaper than barrier.cluster here
     }
     // Payload exchange barrier.  Call pattern inside a collective: thread r (r < nr) has just stored this
     // CTA's payload into CTA r's buffer `par & 1`; it then arrives on CTA r's mbarrier (release, cluster
@@ -535,6 +536,43 @@ __device__ __forceinline__ void c_min3(Coop& c, int& v0, int& v1, int& v2) {
     v0 = r0; v1 = r1; v2 = r2;
 }
 
+// Cluster-wide minimum of one int per thread together with NV doubles held by the (unique) thread that attains it:
+// one exchange.  Every thread returns the minimum and the winner's values.
+template <int NV>
+__device__ __forceinline__ int c_argmin_bcast(Coop& c, int e, const double (&v)[NV], double (&out)[NV]) {
+    static_assert(NV + 1 <= 12 && NV <= 16, "payload slots");
+    Sh& sh = c.sh;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int wm = __reduce_min_sync(0xFFFFFFFFu, e);
+    if (lane == 0) sh.i32[w] = wm;
+    __syncthreads();
+    const int bm = __reduce_min_sync(0xFFFFFFFFu, lane < NW ? sh.i32[lane] : 0x7FFFFFFF);
+    if (e == bm && e != 0x7FFFFFFF) {
+#pragma unroll
+        for (int s = 0; s < NV; ++s) sh.f64[s] = v[s];
+    }
+    __syncthreads();
+    if (c.nr == 1) {
+#pragma unroll
+        for (int s = 0; s < NV; ++s) out[s] = sh.f64[s];
+        return bm;
+    }
+    const unsigned b = c.par & 1u;
+    if (threadIdx.x < c.nr) {
+        long long* dst = c.cl.map_shared_rank(&sh.xl[b][c.rank][0], threadIdx.x);
+        dst[0] = bm;
+#pragma unroll
+        for (int s = 0; s < NV; ++s) dst[1 + s] = __double_as_longlong(sh.f64[s]);
+    }
+    c.xarrive_wait();
+    const int rm = lane < (int)c.nr ? (int)sh.xl[b][lane][0] : 0x7FFFFFFF;
+    const int gm = __reduce_min_sync(0xFFFFFFFFu, rm);
+    const int src = __ffs(__ballot_sync(0xFFFFFFFFu, rm == gm)) - 1;
+#pragma unroll
+    for (int s = 0; s < NV; ++s) out[s] = __longlong_as_double(sh.xl[b][src][1 + s]);
+    return gm;
+}
+
 // ---------------------------------------------------------------------------------------------
 // metric evaluation
 // ---------------------------------------------------------------------------------------------
@@ -635,7 +673,7 @@ __device__ __forceinline__ int local_accepts(const uint32_t (&raw)[DPT], uint32_
 // the stream (the visiting order is irrelevant when the running state cannot change).
 // Part 1 (perm_resolve): the swap targets j[m-1..1] and the stream position after them.
 // Part 2 (perm_apply):   the swap sequence applied to the identity, in parallel.
-__device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
+__device__ void perm_resolve(Coop& c, Pcg& g, int m, int32_t* jarr) {     // jarr == nullptr: stream position only
     const int tid = threadIdx.x;
     if (m <= 1) return;
     // jump constants: 4*gtid LCG steps (this thread's offset in a round) and one full round
@@ -648,8 +686,15 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
     unsigned long long rk = 0ull, pnext = g.has32 ? 1ull : 2ull;
     int i_cur = m - 1;
     long long t0 = clock64();
+#ifdef QA_DBG_PERM
+    long long d_gen = 0, d_sw = 0, d_wr = 0, td;
+    int d_sweeps = 0, d_rounds = 0;
+#endif
     while (i_cur > SEQ_TAIL) {
         ++c.n_rounds;
+#ifdef QA_DBG_PERM
+        __syncthreads(); td = clock64(); ++d_rounds;
+#endif
         const int L = i_cur - SEQ_TAIL;                      // accepts still wanted from the parallel part
         const unsigned long long kb = pnext >> 1;
         if (kb != rk) {
@@ -675,9 +720,25 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
         // every sweep fixes at least one more thread (typically all of them within ~10 sweeps)
         // start from the expected accept count at the current acceptance rate (any start converges: the prefix of
         // thread 0 is exact from the first exchange on, and every sweep fixes at least one more thread)
-        const uint32_t mask0 = 0xFFFFFFFFu >> __clz((uint32_t)i_cur);
-        const double rho = ((double)i_cur + 1.0) / ((double)mask0 + 1.0);
-        int c_in = min(L, (int)(rho * (double)(c.gtid * DPT))), total = 0, a_prev = -1;
+#ifdef QA_DBG_PERM
+        __syncthreads(); d_gen += clock64() - td; td = clock64();
+#endif
+        int c_in, total = 0, a_prev = -1;
+        {
+            // expected accepts among the valid draws before this thread's first one: within a mask bracket the rate is
+            // (i + 1) / (mask + 1) with i falling by one per accept, so c(d) = (i + 1)(1 - exp(-d / (mask + 1)))
+            double dd = (double)(p0 > pnext ? p0 - pnext : 0ull), acc = 0.0;
+            int i = i_cur;
+            while (dd > 0.0 && i > 0) {
+                const uint32_t mk = 0xFFFFFFFFu >> __clz((uint32_t)i);
+                const double mp1 = (double)mk + 1.0;
+                const double A = (double)(i - (int)(mk >> 1));            // accepts until the mask halves
+                const double d_full = -mp1 * log(1.0 - A / ((double)i + 1.0));
+                if (dd >= d_full) { acc += A; i -= (int)A; dd -= d_full; }
+                else { acc += ((double)i + 1.0) * (1.0 - exp(-dd / mp1)); break; }
+            }
+            c_in = min(L, (int)(acc + 0.5));
+        }
         int a = local_accepts(raw, validmask, c_in, i_cur, L);
         for (;;) {
             // one exchange per sweep: prefix of the accept counts + "did any count change since the last sweep";
@@ -690,6 +751,9 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
             c_in = c_new;
             a = local_accepts(raw, validmask, c_in, i_cur, L);
         }
+#ifdef QA_DBG_PERM
+        __syncthreads(); d_sw += clock64() - td; td = clock64();
+#endif
         // write j for the steps this thread resolved; find the draw that supplied the L-th accept
         int done_off = 0x7FFFFFFF;
         {
@@ -700,7 +764,7 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
                 const uint32_t mask = i > 0 ? (0xFFFFFFFFu >> __clz((uint32_t)i)) : 0u;
                 const bool ok = ((validmask >> j) & 1u) && (cc < L) && ((raw[j] & mask) <= (uint32_t)i);
                 if (ok) {
-                    w.jarr[i] = (int32_t)(raw[j] & mask);
+                    if (jarr) jarr[i] = (int32_t)(raw[j] & mask);
                     ++cc;
                     if (cc == L) done_off = c.gtid * DPT + j;
                 }
@@ -713,7 +777,14 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
             pnext = 2ull * (kb + 4ull * (unsigned long long)c.gth);      // every draw of the round was consumed
         }
         i_cur -= total;
+#ifdef QA_DBG_PERM
+        __syncthreads(); d_wr += clock64() - td;
+#endif
     }
+#ifdef QA_DBG_PERM
+    __syncthreads();
+    const long long t_tail0 = clock64();
+#endif
     // sequential tail and stream hand-back: computed redundantly (and identically) by one thread per CTA
     if (tid == 0) {
         const unsigned long long klast = (pnext - 1ull) >> 1;
@@ -727,7 +798,7 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
         t.buf32 = (uint32_t)(pcg_out(s) >> 32);
         for (int i = i_cur; i >= 1; --i) {
             const int32_t j = (int32_t)t.interval((uint32_t)i);
-            if (c.rank == 0) w.jarr[i] = j;
+            if (c.rank == 0 && jarr) jarr[i] = j;
         }
         c.sh.i64[0] = (long long)t.s.hi;
         c.sh.i64[1] = (long long)t.s.lo;
@@ -740,6 +811,10 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, const ParWork& w) {
     g.has32 = (uint32_t)c.sh.i32[3 * NW + 2];
     g.buf32 = (uint32_t)c.sh.i32[3 * NW + 3];
     c.sync();
+#ifdef QA_DBG_PERM
+    if (c.gtid == 0) printf("resolve m=%d rounds %d gen %lld sweeps %lld write+min %lld tail %lld total %lld\n", m, d_rounds, d_gen, d_sw, d_wr,
+                            clock64() - t_tail0, clock64() - t0);
+#endif
     c.cy_resolve += clock64() - t0;
 }
 
@@ -750,10 +825,18 @@ __device__ void perm_apply(Coop& c, int m, const int32_t* cand, int32_t* out, co
         return;
     }
     const long long t0 = clock64();
+#ifdef QA_DBG_PERM
+    long long tp[8]; int np_ = 0;
+#define QA_TP() tp[np_++] = clock64()
+#else
+#define QA_TP()
+#endif
     for (int p = c.gtid; p < m; p += c.gth) w.cursor[p] = 0;
     c.sync();
+    QA_TP();
     for (int i = 1 + c.gtid; i < m; i += c.gth) atomicAdd(&w.cursor[w.jarr[i]], 1);
     c.sync();
+    QA_TP();
     {   // exclusive scan of the per-position counts -> off[], contiguous range per thread
         const int per = (m + c.gth - 1) / c.gth;
         const int b = min(m, c.gtid * per), e = min(m, b + per);
@@ -770,11 +853,13 @@ __device__ void perm_apply(Coop& c, int m, const int32_t* cand, int32_t* out, co
         if (c.gtid == 0) w.off[m] = total;
     }
     c.sync();
+    QA_TP();
     for (int i = 1 + c.gtid; i < m; i += c.gth) {
         const int slot = atomicAdd(&w.cursor[w.jarr[i]], 1);
         w.bucket[slot] = i;
     }
     c.sync();
+    QA_TP();
     for (int p = c.gtid; p < m; p += c.gth) {
         const int b = w.off[p], e = w.off[p + 1];
         for (int a = b + 1; a < e; ++a) {          // insertion sort (buckets hold ~1 entry)
@@ -792,6 +877,7 @@ __device__ void perm_apply(Coop& c, int m, const int32_t* cand, int32_t* out, co
         w.parent[p] = par;       // first later-executed step that writes position p
     }
     c.sync();
+    QA_TP();
     for (int i = c.gtid; i < m; i += c.gth) {
         // a[0] ends as the content of position 0 after all steps; a[i] (i >= 1) is what step i read
         const int start = i == 0 ? w.parent[0] : w.succ[i];
@@ -805,11 +891,16 @@ __device__ void perm_apply(Coop& c, int m, const int32_t* cand, int32_t* out, co
         out[i] = cand ? cand[val] : val;
     }
     c.sync();
+    QA_TP();
+#ifdef QA_DBG_PERM
+    if (c.gtid == 0) printf("apply m=%d zero %lld count %lld scan %lld fill %lld sort %lld follow %lld\n", m, tp[0] - t0, tp[1] - tp[0],
+                            tp[2] - tp[1], tp[3] - tp[2], tp[4] - tp[3], tp[5] - tp[4]);
+#endif
     c.cy_apply += clock64() - t0;
 }
 
 __device__ void permutation_par(Coop& c, Pcg& g, int m, const int32_t* cand, int32_t* out, const ParWork& w, bool apply) {
-    perm_resolve(c, g, m, w);
+    perm_resolve(c, g, m, apply ? w.jarr : nullptr);
     if (apply) perm_apply(c, m, cand, out, w);
     else c.sync();
 }
@@ -824,6 +915,21 @@ __global__ void __launch_bounds__(GT) permutation_par_kernel(qa_pcg64* rng, int 
     if (c.gtid == 0) g.store(rng);
 }
 
+// One permutation's swap targets and the stream state after it (the apply runs as grid kernels, qa_perm_apply.cu)
+__global__ void __launch_bounds__(GT) perm_resolve_kernel(const qa_pcg64* rng_in, int n, int32_t* jarr, qa_pcg64* rng_out) {
+    __shared__ Sh sh;
+    Coop c(sh);
+    Pcg g;
+    g.load(rng_in);
+    c.sync();                       // rng_in may alias rng_out: everyone has read it before rank 0 overwrites it
+    perm_resolve(c, g, n, jarr);
+    if (c.gtid == 0) {
+        rng_out->inc_hi = g.inc.hi;
+        rng_out->inc_lo = g.inc.lo;
+        g.store(rng_out);
+    }
+}
+
 // The first permutations of a greedy run do not depend on the data: the base pass permutes all n tiles (only the
 // stream position matters, the order is irrelevant); unless the base state already fails, pass 2 permutes all n
 // tiles again; and when pass 2 accepts every tile (the usual outcome for the first, nearly lossless candidate
@@ -836,10 +942,10 @@ __global__ void __launch_bounds__(GT) greedy_prefetch_kernel(const qa_pcg64* rng
     Pcg g;
     g.load(rng_in);
     c.sync();
-    perm_resolve(c, g, n, w);                     // permutation #1: stream position only
+    perm_resolve(c, g, n, nullptr);               // permutation #1: stream position only
     for (int k = 0; k + 2 <= npre; ++k) {
         c.sync();                                 // the previous apply has finished reading jarr
-        perm_resolve(c, g, n, w);
+        perm_resolve(c, g, n, w.jarr);
         perm_apply(c, n, nullptr, order_out + (size_t)k * n, w);
         if (c.gtid == 0) {
             rng_out[k].inc_hi = g.inc.hi;
@@ -873,19 +979,17 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
     for (int s = 0; s < NC; ++s) { S[s] = 0.0; events[s] = 0; }
     degraded = 0;
     int pos = min(nt, HEAD);
-    {   // stage the head in shared memory (parallel loads), then one thread adds each column up in order
-        double* stage = reinterpret_cast<double*>(sh.i64);
-        static_assert(sizeof(sh.i64) >= sizeof(double) * HEAD, "head staging does not fit");
+    {   // stage the head in shared memory (parallel loads), then one thread per column adds it up in order
+        static_assert(NC * HEAD <= STAGE_SLOTS * GT, "head staging does not fit");
+        __syncthreads();
 #pragma unroll
-        for (int s = 0; s < NC; ++s) {
-            __syncthreads();
-            if (tid < pos) stage[tid] = col[s][tid];
-            __syncthreads();
-            if (tid == 0) {
-                double acc = 0.0;
-                for (int i = 0; i < pos; ++i) acc = __dadd_rn(acc, stage[i]);
-                sh.f64[s] = acc;
-            }
+        for (int s = 0; s < NC; ++s)
+            if (tid < pos) qa_stage[s * HEAD + tid] = col[s][tid];
+        __syncthreads();
+        if (tid < NC) {
+            double acc = 0.0;
+            for (int i = 0; i < pos; ++i) acc = __dadd_rn(acc, qa_stage[tid * HEAD + i]);
+            sh.f64[tid] = acc;
         }
     }
     __syncthreads();
@@ -934,54 +1038,41 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
             for (int s = 0; s < NC; ++s) tot[s] = p2_then(tot[s], p[s]);
         }
         scan_totals<NC>(c, tot, pre0);
-        // walk 2: first element whose result leaves a binade (its own add is still exact)
-        int cut = len - 1, unused = 0x7FFFFFFF;
-        {
-            P2 run[NC];
+        // walk 2: this thread's first element that ends the chunk - one that cannot ride the grid, one whose result
+        // leaves a binade, or the chunk's last element - and the state after it, fl(S_before + t): a real add from
+        // the exact state before it.  The cluster-wide first such element wins.
+        int e_l = 0x7FFFFFFF;
+        double cand_nv[NC], nv[NC];
 #pragma unroll
-            for (int s = 0; s < NC; ++s) run[s] = pre0[s];
-            for (int idx = lo; idx < hi && idx < bad; ++idx) {
+        for (int s = 0; s < NC; ++s) cand_nv[s] = 0.0;
+        {
+            P2 run[NC], prev[NC];
+#pragma unroll
+            for (int s = 0; s < NC; ++s) run[s] = prev[s] = pre0[s];
+            for (int idx = lo; idx < hi; ++idx) {
+#pragma unroll
+                for (int s = 0; s < NC; ++s) prev[s] = run[s];
+                if (idx == bad) { e_l = idx; break; }
+                bool leaves = false;
 #pragma unroll
                 for (int s = 0; s < NC; ++s) {
                     if ((degraded >> s) & 1u) continue;
                     P2 p{0, 0};
                     classify(g[s], staged(s, idx - lo), p);
                     run[s] = p2_then(run[s], p);
-                    if (g[s].q != 0.0 && !in_binade(m_after(g[s], run[s]))) cut = min(cut, idx);
+                    if (g[s].q != 0.0 && !in_binade(m_after(g[s], run[s]))) leaves = true;
                 }
-                if (cut == idx) break;
+                if (leaves || idx == len - 1) { e_l = idx; break; }
             }
-        }
-        c_min3(c, bad, cut, unused);
-        cut = min(cut, bad);
-        // state after element `cut` = fl(S_before(cut) + t_cut): a real add from the exact state before it
-        double nv[NC];
-        {
-            const bool owner = cut >= lo && cut < lo + per;
-            double vals[NC];
-#pragma unroll
-            for (int s = 0; s < NC; ++s) vals[s] = 0.0;
-            if (owner) {
-                P2 run[NC];
-#pragma unroll
-                for (int s = 0; s < NC; ++s) run[s] = pre0[s];
-                for (int idx = lo; idx < cut; ++idx) {
-#pragma unroll
-                    for (int s = 0; s < NC; ++s) {
-                        if ((degraded >> s) & 1u) continue;
-                        P2 p{0, 0};
-                        classify(g[s], staged(s, idx - lo), p);
-                        run[s] = p2_then(run[s], p);
-                    }
-                }
+            if (e_l != 0x7FFFFFFF) {
 #pragma unroll
                 for (int s = 0; s < NC; ++s) {
-                    const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], run[s])) : S[s];
-                    vals[s] = __dadd_rn(before, staged(s, cut - lo));
+                    const double before = g[s].q != 0.0 ? s_of(g[s], m_after(g[s], prev[s])) : S[s];
+                    cand_nv[s] = __dadd_rn(before, staged(s, e_l - lo));
                 }
             }
-            c_bcast_d(c, owner, vals, NC, nv);
         }
+        const int cut = c_argmin_bcast<NC>(c, e_l, cand_nv, nv);
         const bool cut_short = cut < len - 1;
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
@@ -1062,16 +1153,18 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
     }
     // delta[tr][t] = stats(fmt[tr+1]) - stats(fmt[tr]) of tile t: one 32-byte record per tile and transition, so the
     // chain fetches a visited tile with one sector instead of eight
-    for (int tr = 0; tr + 1 < ord.n; ++tr) {
-        const int f0 = ord.fmt[tr], f1 = ord.fmt[tr + 1];
-        double2* dst = reinterpret_cast<double2*>(delta + (size_t)tr * nt * 4);
-        for (int t = c.gtid; t < nt; t += c.gth) {
-            double d[4];
+    for (int t = c.gtid; t < nt; t += c.gth) {
+        double v[QA_NFMT][4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                d[q] = __dsub_rn(table[(size_t)QA_STAT_FMT(f1, q) * nt + t], table[(size_t)QA_STAT_FMT(f0, q) * nt + t]);
-            dst[2 * (size_t)t] = make_double2(d[0], d[1]);
-            dst[2 * (size_t)t + 1] = make_double2(d[2], d[3]);
+        for (int f = 0; f < QA_NFMT; ++f)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[f][q] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], q) * nt + t] : 0.0;
+#pragma unroll
+        for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
+            if (tr + 1 >= ord.n) break;
+            double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
+            dst[0] = make_double2(__dsub_rn(v[tr + 1][0], v[tr][0]), __dsub_rn(v[tr + 1][1], v[tr][1]));
+            dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
         }
     }
     if (c.gtid == 0) {
@@ -1446,9 +1539,18 @@ static int pick_cluster(int64_t n) {
 
 template <typename... KArgs, typename... Args>
 static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
-    if (nr > 8) cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     constexpr int dyn = STAGE_SLOTS * GT * (int)sizeof(double);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    {   // attributes are set once per kernel (not a stream operation: keep it out of the per-launch path and of graph captures)
+        static void* done[32];
+        static int ndone = 0;
+        bool seen = false;
+        for (int i = 0; i < ndone; ++i) seen = seen || done[i] == (void*)kern;
+        if (!seen) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+            if (ndone < 32) done[ndone++] = (void*)kern;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nr, 1, 1);
     cfg.blockDim = dim3(GT, 1, 1);
@@ -1489,6 +1591,11 @@ extern "C" int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_p
     if (!rng || n < 0 || n > 0x3FFFFFFF || (n > 0 && (!out_perm || !work))) { set_error("qa_numpy_permutation_par: bad args"); return 1; }
     if (n == 0) return 0;
     return launch_cluster(permutation_par_kernel, pick_cluster(n), (cudaStream_t)stream, rng, (int)n, out_perm, carve(work, n));
+}
+
+extern "C" int qa_perm_resolve(const qa_pcg64* rng_in, int64_t n, int32_t* jarr, qa_pcg64* rng_out, qa_stream_t stream) {
+    if (!rng_in || !rng_out || n <= 0 || n > 0x3FFFFFFF) { set_error("qa_perm_resolve: bad args"); return 1; }
+    return launch_cluster(perm_resolve_kernel, pick_cluster(n), (cudaStream_t)stream, rng_in, (int)n, jarr, rng_out);
 }
 
 extern "C" int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int nfmt, int32_t* pre_order, qa_pcg64* pre_rng, void* work,

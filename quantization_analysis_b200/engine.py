@@ -206,6 +206,20 @@ def greedy_prefetch(rng: torch.Tensor, ntiles: int, work: torch.Tensor | None = 
     return pre_order, pre_rng
 
 
+def numpy_permutation_staged(rng: torch.Tensor, n: int) -> torch.Tensor:
+    """numpy permutation(n) as qa_perm_resolve (one cluster) + qa_perm_apply (grid kernels); advances `rng`."""
+    L = _lib.lib()
+    dev = rng.device
+    jarr = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    out = torch.empty(n, dtype=torch.int32, device=dev)
+    if n == 0:
+        return out
+    work = torch.empty(L.qa_perm_apply_work_bytes(n), dtype=torch.uint8, device=dev)
+    check(L.qa_perm_resolve(_ptr(rng), n, _ptr(jarr), _ptr(rng), _stream()), "qa_perm_resolve")
+    check(L.qa_perm_apply(_ptr(jarr), n, None, _ptr(out), _ptr(work), _stream()), "qa_perm_apply")
+    return out
+
+
 def greedy_init(table: torch.Tensor, metric: str, fmt_order) -> torch.Tensor:
     """Initial sums + per-transition delta records of a greedy run (qa_greedy_init); consumed by greedy_assign(init=...)."""
     L = _lib.lib()

@@ -334,6 +334,21 @@ def test_parallel_greedy_degenerate_inputs(qa, kind):
             assert np.array_equal(s1.cpu().numpy()[:5], s2.cpu().numpy()[:5])
 
 
+def test_staged_permutation_matches_numpy(qa):
+    """qa_perm_resolve (cluster) + qa_perm_apply (grid kernels) == numpy Generator.permutation, stream position included."""
+    eng = qa["engine"]
+    for seed, n in ((3, 0), (3, 1), (3, 2), (4, 97), (5, 98), (6, 5000), (7, 40000), (123, 114688)):
+        r1, r2 = eng.make_rng(seed), eng.make_rng(seed)
+        got = eng.numpy_permutation_staged(r1, n).cpu().numpy()
+        gen = np.random.default_rng(seed)
+        want = gen.permutation(n)
+        assert np.array_equal(got, want), (seed, n)
+        # same stream position afterwards: the next draws agree
+        nxt = eng.numpy_permutation(r1, 50, parallel=False).cpu().numpy()
+        assert np.array_equal(nxt, gen.permutation(50)), (seed, n)
+        eng.numpy_permutation(r2, n, parallel=False)
+
+
 def test_greedy_staged_equals_inline(qa):
     """qa_greedy_prefetch / qa_greedy_init + qa_greedy_assign_par_pre give the same map, counts, state and stream
     position as the kernel that does everything inline, in every combination of stages - including a base state that
@@ -441,3 +456,28 @@ def test_random_bit_patterns_property(qa):
         with np.errstate(all="ignore"):
             for fmt in ("bf16", "bfp8", "bfp4", "bfp2"):
                 assert np.array_equal(G.bits(qf.quantize_weight_values(x, fmt)), G.bits(orc.quantize(x, fmt))), (trial, shape, fmt)
+
+
+def test_batch_graph_replay_equals_eager(qa):
+    """GreedyBatch.run_graph (one captured CUDA graph per pass) gives the same maps / counts / states as eager enqueueing,
+    and replays pick up newly loaded inputs."""
+    import torch
+    from quantization_analysis_b200.batch import GreedyBatch
+    from quantization_analysis_b200 import synthetic
+    shapes = [(256, 512), (96, 320), (512, 256)]
+    xs = [synthetic.randn_bf16_cpu(s, 40 + i) for i, s in enumerate(shapes)]
+    xs2 = [synthetic.randn_bf16_cpu(s, 50 + i) for i, s in enumerate(shapes)]
+    b = GreedyBatch(shapes, metric="pcc", threshold=0.999, seed=9)
+    for data in (xs, xs2):
+        b.load_device(data)
+        b.run()
+        eager = b.collect()
+        for s in b.slots:
+            s["assignment"].fill_(-1)
+            s["counts"].zero_()
+        b.run_graph()
+        graph = b.collect()
+        for e, g in zip(eager, graph):
+            assert np.array_equal(e["assignment"], g["assignment"])
+            assert e["counts"] == g["counts"]
+            assert np.array_equal(e["state"][:8], g["state"][:8])
