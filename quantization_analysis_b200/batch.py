@@ -24,7 +24,9 @@ class GreedyBatch:
         self.tile_formats = list(tile_formats)
         self.shapes = [tuple(int(v) for v in s) for s in shapes]
         n_streams = min(16, len(self.shapes)) if n_streams is None else n_streams     # one stream per tensor
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        # the first stream carries the largest tensor (run() enqueues longest chain first): its kernels go first when
+        # blocks of several tensors compete for SMs, since that chain is the critical path of the step
+        self.streams = [torch.cuda.Stream(device=self.device, priority=-1 if i == 0 else 0) for i in range(max(1, n_streams))]
         self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
         self.side2_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
         self.prefetch = metric != "atol" and len(self.tile_formats) >= 2

@@ -39,7 +39,7 @@ constexpr int GT = 512;           // threads per CTA
 constexpr int NW = GT / 32;
 constexpr int MAXR = 16;          // largest cluster
 constexpr int DPT = 8;            // draws per thread per round (4 LCG outputs)
-constexpr int EPS = 4;           // elements each thread streams through per chunk (scan works on thread totals)
+constexpr int EPS = 8;           // elements each thread streams through per chunk (scan works on thread totals)
 constexpr int SEQ_TAIL = 96;      // last Fisher-Yates steps are drawn by one thread
 constexpr long long M_LO = 1ll << 52, M_HI = 1ll << 53;
 
@@ -65,6 +65,11 @@ struct ParWork {
     int npre;                   // how many permutations were drawn ahead (0, 2 or 3)
 };
 constexpr int HDR_DOUBLES = 32;
+#ifdef QA_DBG_CHAIN
+#define QA_PHASE_SYNC() __syncthreads()
+#else
+#define QA_PHASE_SYNC()
+#endif
 
 struct P2 {          // increment of m if the incoming m is even / odd
     long long d0, d1;
@@ -1153,6 +1158,9 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
     }
     // delta[tr][t] = stats(fmt[tr+1]) - stats(fmt[tr]) of tile t: one 32-byte record per tile and transition, so the
     // chain fetches a visited tile with one sector instead of eight
+    double dr[QA_NFMT - 1];                      // per transition: sum |delta sy| over all tiles (bounds the drift of sy)
+#pragma unroll
+    for (int tr = 0; tr + 1 < QA_NFMT; ++tr) dr[tr] = 0.0;
     for (int t = c.gtid; t < nt; t += c.gth) {
         double v[QA_NFMT][4];
 #pragma unroll
@@ -1163,11 +1171,18 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
         for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
             if (tr + 1 >= ord.n) break;
             double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
-            dst[0] = make_double2(__dsub_rn(v[tr + 1][0], v[tr][0]), __dsub_rn(v[tr + 1][1], v[tr][1]));
+            const double d0 = __dsub_rn(v[tr + 1][0], v[tr][0]);
+            dr[tr] += fabs(d0);
+            dst[0] = make_double2(d0, __dsub_rn(v[tr + 1][1], v[tr][1]));
             dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
         }
     }
+#pragma unroll
+    for (int tr = 0; tr + 1 < QA_NFMT; ++tr)
+        if (PCC && tr + 1 < ord.n) dr[tr] = c_reduce_d<false>(c, dr[tr]);
     if (c.gtid == 0) {
+#pragma unroll
+        for (int tr = 0; tr + 1 < QA_NFMT; ++tr) hdr[11 + tr] = dr[tr];
         hdr[0] = sx; hdr[1] = sx2; hdr[2] = S[0]; hdr[3] = S[1]; hdr[4] = S[2]; hdr[5] = S[3];
         hdr[6] = (double)degraded;
         hdr[7] = (double)(clock64() - t_start);
@@ -1226,27 +1241,68 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     unsigned n_chunks = 0, n_cutshort = 0;
     const long long cyc_init = have_init ? (long long)w.hdr[7] : t_mark - t_start;
     const int CHc = c.gth * EPS;
+    bool base_failed = false, all_tiles_candidates = true;
+    int accepted_last = nt;
 
     for (int fi = 0; fi < ord.n; ++fi) {
         const int fmt = ord.fmt[fi];
         // ---- candidates = not-fixed tiles in ascending order ------------------------------
+        // The base pass fixes every tile or none, and a pass that accepted all of its candidates fixes none: as long
+        // as that holds the candidates are the tiles 0..nt-1 themselves and no list is built (cand == nullptr).
         int m;
-        {
-            const int per = (nt + c.gth - 1) / c.gth;
-            const int b = min(nt, c.gtid * per), e = min(nt, b + per);
-            int local = 0;
-            for (int t = b; t < e; ++t) local += w.fixed[t] ? 0 : 1;
-            int run = c_scan_excl(c, local, m);
-            for (int t = b; t < e; ++t)
-                if (!w.fixed[t]) w.cand[run++] = t;
+        const int32_t* cand = nullptr;
+        if (fi == 0) m = nt;
+        else if (fi == 1) m = base_failed ? 0 : nt;
+        else if (all_tiles_candidates && accepted_last == nt) m = nt;
+        else {
+            all_tiles_candidates = false;
+            const int lane = tid & 31;
+            const int nwarps = c.gth >> 5, gw = c.gtid >> 5;
+            const int per_w = (((nt + nwarps - 1) / nwarps) + 31) & ~31;        // a multiple of 32 tiles per warp
+            const int b = min(nt, gw * per_w), e = min(nt, b + per_w);
+            int cntw = 0;
+            for (int t0 = b; t0 < e; t0 += 32) {
+                const int t = t0 + lane;
+                cntw += __popc(__ballot_sync(0xFFFFFFFFu, t < e && !w.fixed[t]));
+            }
+            int run = c_scan_excl(c, lane == 0 ? cntw : 0, m);                  // lane 0: candidates in earlier warps
+            run = __shfl_sync(0xFFFFFFFFu, run, 0);
+            for (int t0 = b; t0 < e; t0 += 32) {
+                const int t = t0 + lane;
+                const bool keep = t < e && !w.fixed[t];
+                const unsigned bal = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) w.cand[run + __popc(bal & ((1u << lane) - 1u))] = t;
+                run += __popc(bal);
+            }
+            cand = w.cand;
+            c.sync();
         }
-        c.sync();
         if (m == 0) {
             // the base pass fixed every tile: only permutation #1 was consumed (rare; redo it if it was prefetched away)
-            if (fi == 1 && w.pre_order != nullptr && w.npre >= 2 && ord.n >= 2) permutation_par(c, g, nt, w.cand, w.order, w, false);
+            if (fi == 1 && w.pre_order != nullptr && w.npre >= 2 && ord.n >= 2) permutation_par(c, g, nt, nullptr, w.order, w, false);
             break;
         }
+        int my_accepts = 0;                              // accepted by this thread during the pass
         const bool base_pass = fi == 0;
+        // every candidate of pass fi was accepted in pass fi-1 (rejected tiles are fixed), so its
+        // current format is the previous one in the order
+        const int prev = base_pass ? base : ord.fmt[fi - 1];
+        const double* dtab = w.delta + (size_t)(base_pass ? 0 : fi - 1) * nt * 4;      // {d sy, d sy2, d sxy, d sabs} per tile
+        // sy is a signed sum near its mean: if the pass could carry it across a binade boundary (or zero),
+        // run it on a fixed coarser grid instead of cutting a chunk at every hop
+        bool relax_sy = false;
+        double drift = 0.0;                              // sum |delta sy| over the candidates: how far sy can move
+        if (PCC && !base_pass) {
+            tq = clock64();
+            if (cand == nullptr) drift = w.hdr[11 + fi - 1];      // every tile is a candidate: summed by the init phase
+            else {
+                for (int q = c.gtid; q < m; q += c.gth) drift += fabs(dtab[4 * (size_t)cand[q]]);
+                drift = c_reduce_d<false>(c, drift);
+            }
+            relax_sy = !stays_in_binade(S[0], drift);
+            if (relax_sy) degraded |= 4u;
+            cy_gather += clock64() - tq;
+        }
         // ---- (2) visiting order ----------------------------------------------------------
         t_mark = clock64();
         const bool have_pre = w.pre_order != nullptr && w.npre >= 2 && ord.n >= 2;
@@ -1260,7 +1316,44 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             order_ptr = w.pre_order + nt;     // pass 2 accepted every tile: the speculative third permutation applies
             g.load(w.pre_rng + 1);
         } else {
-            permutation_par(c, g, m, w.cand, w.order, w, !base_pass);
+            // Order-free shortcut: the state only changes on an accept, so if no candidate passes against the state at
+            // the start of the pass, every candidate sees exactly that state whatever the visiting order and all are
+            // rejected.  Then only the stream position of the permutation is needed, not the permutation itself.
+            bool none = false;
+            double sb0_start = S[0];
+            if (!base_pass) {
+                double sb0 = S[0];
+                if (PCC && relax_sy) {
+                    const Grid gx = make_grid_relaxed(S[0], drift);
+                    if (gx.q != 0.0) sb0 = s_of(gx, gx.m0);          // the chain starts from the grid-rounded value
+                    sb0_start = sb0;
+                }
+                auto passes = [&](int q) -> bool {
+                    const double2* rec = reinterpret_cast<const double2*>(dtab) + 2 * (size_t)(cand ? cand[q] : q);
+                    const double2 ra = rec[0], rb = rec[1];
+                    double cnd[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (PCC) {
+                        cnd[0] = __dadd_rn(sb0, ra.x); cnd[1] = __dadd_rn(S[1], ra.y); cnd[2] = __dadd_rn(S[2], rb.x);
+                        cnd[3] = S[3] + rb.y;
+                    } else cnd[3] = __dadd_rn(S[3], rb.y);
+                    return good_par(k, cnd);
+                };
+                bool acc = c.gtid < m && passes(c.gtid);              // a sample first: passes that do accept stop here
+                if (!c_any(c, acc)) {
+                    for (int q = c.gtid + c.gth; q < m && !acc; q += c.gth) acc = passes(q);
+                    none = !c_any(c, acc);
+                }
+            }
+            if (none) {
+                if (PCC && relax_sy) S[0] = sb0_start;              // what an all-reject chain leaves behind
+                perm_resolve(c, g, m, nullptr);
+                for (int q = c.gtid; q < m; q += c.gth) w.fixed[cand ? cand[q] : q] = 1;
+                c.sync();
+                cyc_perm += clock64() - t_mark;
+                accepted_last = 0;
+                continue;
+            }
+            permutation_par(c, g, m, cand, w.order, w, !base_pass);
         }
         cyc_perm += clock64() - t_mark;
         t_mark = clock64();
@@ -1268,28 +1361,12 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             // every candidate already has this format: the state cannot change, so all of them see the
             // same test (mixed_tile_greedy.py:238-241)
             if (!good_par(k, S)) {
-                for (int q = c.gtid; q < m; q += c.gth) w.fixed[w.cand[q]] = 1;
+                for (int q = c.gtid; q < m; q += c.gth) w.fixed[q] = 1;
+                base_failed = true;
             }
             c.sync();
             continue;
         }
-        // every candidate of pass fi was accepted in pass fi-1 (rejected tiles are fixed), so its
-        // current format is the previous one in the order
-        const int prev = ord.fmt[fi - 1];
-        const double* dtab = w.delta + (size_t)(fi - 1) * nt * 4;      // {d sy, d sy2, d sxy, d sabs} per tile
-        tq = clock64();
-        // sy is a signed sum near its mean: if the pass could carry it across a binade boundary (or zero),
-        // run it on a fixed coarser grid instead of cutting a chunk at every hop
-        bool relax_sy = false;
-        double drift = 0.0;                              // sum |delta sy| over the candidates: how far sy can move
-        if (PCC) {
-            for (int t = c.gtid; t < nt; t += c.gth)
-                if (!w.fixed[t]) drift += fabs(dtab[4 * (size_t)t]);
-            drift = c_reduce_d<false>(c, drift);
-            relax_sy = !stays_in_binade(S[0], drift);
-            if (relax_sy) degraded |= 4u;
-        }
-        cy_gather += clock64() - tq;
         // ---- (3) accept / reject chain -------------------------------------------------------
         int pos = 0;
         bool guess = true;                      // initial guess for a chunk: accept everything
@@ -1305,14 +1382,21 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             unsigned D = 0;
             int valid = len;
             P2 pre0[NS];
+            double st_rej[NS], st_take[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) st_rej[s] = st_take[s] = 0.0;
+            bool pathological = false;
             bool any_flag = guess;             // uniform: does any element of the chunk carry an accept flag?
+            int tl[EPS];                       // the tiles this thread visits in this chunk
+#pragma unroll
+            for (int j = 0; j < EPS; ++j) tl[j] = j < cnt ? order_ptr[pos + lo + j] : 0;
             {   // fetch the visited tiles' delta records (one 32-byte sector each)
                 double2 da[EPS], db[EPS];
 #pragma unroll
                 for (int j = 0; j < EPS; ++j) {
                     da[j] = db[j] = make_double2(0.0, 0.0);
                     if (j < cnt) {
-                        const double2* rec = reinterpret_cast<const double2*>(dtab) + 2 * (size_t)order_ptr[pos + lo + j];
+                        const double2* rec = reinterpret_cast<const double2*>(dtab) + 2 * (size_t)tl[j];
                         if (PCC) da[j] = rec[0];
                         db[j] = rec[1];
                     }
@@ -1323,7 +1407,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                     else staged(0, j) = db[j].y;
                 }
             }
-            cy_load += clock64() - tq;
+            QA_PHASE_SYNC(); cy_load += clock64() - tq;
             for (int round = 0; round < 64; ++round) {
                 ++chain_rounds;
                 tq = clock64();
@@ -1347,7 +1431,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
 #pragma unroll
                     for (int s = 0; s < NS; ++s) pre0[s] = P2{0, 0};
                 }
-                cy_scan += clock64() - tq; tq = clock64();
+                QA_PHASE_SYNC(); cy_scan += clock64() - tq; tq = clock64();
                 // walk 2: exact state before every element -> decision; first wrong flag; first binade exit
                 int mism = 0x7FFFFFFF, cut = 0x7FFFFFFF;
                 D = 0;
@@ -1363,6 +1447,8 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                             dl[s] = staged(s, j);
                             const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
                             cnd[S0 + s] = __dadd_rn(sb, dl[s]);
+                            st_rej[s] = sb;                 // state after this element if it is rejected / accepted:
+                            st_take[s] = cnd[S0 + s];       // kept for the commit (the last element a thread walks)
                         }
                         if (PCC) cnd[3] = S[3] + staged(3, j);          // chunk-start value: only its zero test matters
                         const bool dj = good_par(k, cnd);
@@ -1382,22 +1468,22 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
                         }
                     }
                 }
-                cy_dec += clock64() - tq; tq = clock64();
+                QA_PHASE_SYNC(); cy_dec += clock64() - tq; tq = clock64();
                 // third slot: 0 if any element would carry an accept flag in the next round (F below mism, D from it on)
-                int next_any = 0x7FFFFFFF;
-                for (int j = 0; j < cnt && lo + j < valid; ++j)
-                    if ((D >> j) & 1u || (F >> j) & 1u) next_any = 0;
-                c_min3(c, mism, cut, next_any);
-                cy_min += clock64() - tq;
+                const int nval = max(0, min(cnt, valid - lo));
+                const int next_any = ((D | F) & (nval > 0 ? (0xFFFFFFFFu >> (32 - nval)) : 0u)) ? 0 : 0x7FFFFFFF;
+                int next_any_io = next_any;
+                c_min3(c, mism, cut, next_any_io);
+                QA_PHASE_SYNC(); cy_min += clock64() - tq;
                 cut = min(cut, valid - 1);
                 if (mism > cut) { valid = cut + 1; break; }       // flags are consistent up to the cut
-                if (round == 63) { valid = mism + 1; }            // pathological: commit up to the first wrong flag
+                if (round == 63) { valid = mism + 1; pathological = true; }   // commit up to the first wrong flag
                 // fix the first wrong flag; later ones take the freshly computed decisions as the new guess
                 for (int j = 0; j < cnt; ++j) {
                     const int idx = lo + j;
                     if (idx >= mism && idx < valid) F = (F & ~(1u << j)) | (D & (1u << j));
                 }
-                any_flag = next_any == 0;       // conservative (a superset of the flags actually set)
+                any_flag = next_any_io == 0;    // conservative (a superset of the flags actually set)
                 if (round == 63) break;
             }
             // ---- commit [0, valid): D holds the decisions; pre0 the exact prefix of this thread ----
@@ -1406,37 +1492,46 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             bool owner = false;
             double vals[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
             double dabs = 0.0;
-            for (int j = 0; j < cnt && lo + j < valid; ++j) {
-                const int t = order_ptr[pos + lo + j];
-                if ((D >> j) & 1u) {
-                    assignment[t] = (int8_t)fmt;
-                    ++loc;
-                    if (PCC) dabs += staged(3, j);
-                } else w.fixed[t] = 1;
+#pragma unroll
+            for (int j = 0; j < EPS; ++j) {
+                if (j < cnt && lo + j < valid) {
+                    if ((D >> j) & 1u) {
+                        assignment[tl[j]] = (int8_t)fmt;
+                        ++loc;
+                        if (PCC) dabs += staged(3, j);
+                    } else w.fixed[tl[j]] = 1;
+                }
             }
             if (valid - 1 >= lo && valid - 1 < lo + EPS) {       // owner of the last committed element
                 owner = true;
-                P2 run[NS];
-#pragma unroll
-                for (int s = 0; s < NS; ++s) run[s] = pre0[s];
                 const int jl = valid - 1 - lo;
-                for (int j = 0; j < jl; ++j) {
-                    if (!((D >> j) & 1u)) continue;
+                const bool take = (D >> jl) & 1u;
+                if (!pathological) {
+                    // the last element this thread walked in the final round is valid - 1: its two outcomes are at hand
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) vals[S0 + s] = take ? st_take[s] : st_rej[s];
+                } else {
+                    P2 run[NS];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) run[s] = pre0[s];
+                    for (int j = 0; j < jl; ++j) {
+                        if (!((D >> j) & 1u)) continue;
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            P2 p{0, 0};
+                            classify(gr[s], staged(s, j), p);
+                            run[s] = p2_then(run[s], p);
+                        }
+                    }
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        P2 p{0, 0};
-                        classify(gr[s], staged(s, j), p);
-                        run[s] = p2_then(run[s], p);
+                        const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
+                        vals[S0 + s] = take ? __dadd_rn(sb, staged(s, jl)) : sb;
                     }
-                }
-                const bool take = (D >> jl) & 1u;
-#pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    const double sb = gr[s].q != 0.0 ? s_of(gr[s], m_after(gr[s], run[s])) : S[S0 + s];
-                    vals[S0 + s] = take ? __dadd_rn(sb, staged(s, jl)) : sb;
                 }
                 vals[4] = take ? 1.0 : 0.0;
             }
+            my_accepts += loc;
             loc = __reduce_add_sync(0xFFFFFFFFu, loc);
             if ((tid & 31) == 0 && loc) { atomicAdd(&sh.cnt[fmt], loc); atomicAdd(&sh.cnt[prev], -loc); }
             double nv[5];
@@ -1448,8 +1543,9 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
             ++n_chunks;
             if (valid < len) ++n_cutshort;
             pos += valid;
-            cy_commit += clock64() - tq;
+            QA_PHASE_SYNC(); cy_commit += clock64() - tq;
         }
+        if (fi + 1 < ord.n) accepted_last = (int)c_reduce_d<false>(c, (double)my_accepts);     // exact: counts < 2^53
         cyc_chain += clock64() - t_mark;
     }
     // max |x - y| of the final assignment (for the reported atol)
@@ -1472,6 +1568,9 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         state[16] = (double)(clock64() - t_start); state[17] = (double)cy_commit; state[18] = (double)cy_gather;
         state[19] = (double)n_chunks; state[20] = (double)n_cutshort;
         state[13] = w.hdr[8]; state[14] = w.hdr[9]; state[15] = w.hdr[10];
+#ifdef QA_DBG_CHAIN
+        printf("chain nt=%d load %lld walk1+scan %lld decide %lld min3 %lld commit %lld gather %lld | chunks %u rounds %u total %lld\n", nt, cy_load, cy_scan, cy_dec, cy_min, cy_commit, cy_gather, n_chunks, chain_rounds, (long long)(clock64() - t_start));
+#endif
         state[21] = (double)c.cy_resolve; state[22] = (double)c.cy_apply; state[23] = (double)c.n_sweeps + 65536.0 * c.n_rounds;
     }
 }
