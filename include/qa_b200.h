@@ -139,6 +139,10 @@ int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_perm, void* 
  *  qa_perm_apply   - out[k] = cand ? cand[perm[k]] : perm[k] from the swap targets, as grid kernels on the whole GPU.
  *      work: at least qa_perm_apply_work_bytes(n) bytes. */
 int qa_perm_resolve(const qa_pcg64* rng_in, int64_t n, int32_t* jarr, qa_pcg64* rng_out, qa_stream_t stream);
+/* `count` consecutive permutations of n items from one stream in one launch: jarr int32[count][n] (row k written iff bit k
+ * of write_mask), rng_out[count] = stream state after each.  rng_out must not alias rng_in. */
+int qa_perm_resolve_chain(const qa_pcg64* rng_in, int64_t n, int count, uint32_t write_mask, int32_t* jarr,
+                          qa_pcg64* rng_out, qa_stream_t stream);
 int64_t qa_perm_apply_work_bytes(int64_t n);
 int qa_perm_apply(const int32_t* jarr, int64_t n, const int32_t* cand, int32_t* out, void* work,
                   qa_stream_t stream);

@@ -24,11 +24,18 @@ class GreedyBatch:
         self.tile_formats = list(tile_formats)
         self.shapes = [tuple(int(v) for v in s) for s in shapes]
         n_streams = min(16, len(self.shapes)) if n_streams is None else n_streams     # one stream per tensor
-        # the first stream carries the largest tensor (run() enqueues longest chain first): its kernels go first when
-        # blocks of several tensors compete for SMs, since that chain is the critical path of the step
-        self.streams = [torch.cuda.Stream(device=self.device, priority=-1 if i == 0 else 0) for i in range(max(1, n_streams))]
-        self.side_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        # Cluster kernels (resolve / init / chain) can only start when a whole GPC's worth of SMs is free at once, which a
+        # streaming kernel that keeps refilling every SM rarely allows: they go on high-priority streams, the tile-stat
+        # kernels on normal-priority ones, so the block scheduler drains SMs for a pending cluster first.
+        self.streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(1, n_streams))]
+        self.side_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(1, n_streams))]
         self.side2_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        # The tile-stat kernels are bandwidth-bound and each fills the GPU: run concurrently they only slow each other
+        # down, and the largest tensor - whose init/chain is the critical path - would get its table last.  A short
+        # list of large tensors therefore streams its tile-stat passes one after the other, largest first; a long list
+        # of small ones (one MoE layer = 768 tensors) keeps a few streams to hide launch gaps.
+        self.stats_streams = [torch.cuda.Stream(device=self.device) for _ in range(1 if len(self.shapes) <= 16 else 4)]
+        self._stats_rr = 0
         self.prefetch = metric != "atol" and len(self.tile_formats) >= 2
         L = _lib.lib()
         self.slots = []
@@ -47,24 +54,24 @@ class GreedyBatch:
                                     device=self.device),
                 "rng": rng0.clone(),
                 "pre_order": torch.empty((2, nt), dtype=torch.int32, device=self.device),
-                "pre_rng": torch.stack([rng0, rng0]).contiguous(),
+                "rngs": torch.stack([rng0, rng0, rng0]).contiguous(),      # stream states after permutations #1, #2, #3
                 "init": torch.empty(L.qa_greedy_init_bytes(nt), dtype=torch.uint8, device=self.device),
-                "jarr": torch.empty((2, nt), dtype=torch.int32, device=self.device),
-                "rng1": rng0.clone(),
+                "jarr": torch.empty((3, nt), dtype=torch.int32, device=self.device),
                 "apply_work": torch.empty((2, L.qa_perm_apply_work_bytes(nt)), dtype=torch.uint8, device=self.device),
                 "ev": torch.cuda.Event(),
             })
         self._rng0 = rng0
         self._graphs = {}
+        self.trace = None            # set to {} to record per-tensor stage events during eager run() (see timeline())
         self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
         # kernels of ours per tensor and step.  atol: tile_stats + greedy + assignment_sums.  pcc / mae: tile_stats +
-        # greedy_init + greedy chain, plus the prefetched permutations (a resolve kernel each, 7 grid kernels per apply)
+        # greedy_init + greedy chain, plus the prefetched permutations (one chained resolve kernel, 7 grid kernels per apply)
         if metric == "atol":
             per_tensor = 3
         elif not self.prefetch:
             per_tensor = 3
         else:
-            per_tensor = 3 + (3 + 2 * 7 if len(self.tile_formats) >= 3 else 2 + 7)
+            per_tensor = 3 + (1 + 2 * 7 if len(self.tile_formats) >= 3 else 1 + 7)
         self.launches_per_step = per_tensor * len(self.slots)
 
     # ---- data movement -------------------------------------------------------------------
@@ -81,6 +88,14 @@ class GreedyBatch:
         L = _lib.lib()
         sp = stream.cuda_stream
         pre = assign and self.prefetch and side is not None
+
+        def mark(tag, on=None):
+            if self.trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(on or stream)
+                self.trace.setdefault(id(slot), {})[tag] = ev
+
+        mark("start")
         if pre:
             # the first permutations depend only on (seed, ntiles): draw them on side streams while the tile-stat pass
             # streams the tensor.  Resolves chain through the RNG state (#1 -> #2 -> #3, one cluster each); each apply
@@ -89,25 +104,32 @@ class GreedyBatch:
             n, three = slot["ntiles"], len(self.tile_formats) >= 3
             side.wait_stream(stream)
             sa = side.cuda_stream
-            check(L.qa_perm_resolve(self._rng0.data_ptr(), n, None, slot["rng1"].data_ptr(), sa), "qa_perm_resolve")
-            check(L.qa_perm_resolve(slot["rng1"].data_ptr(), n, slot["jarr"][0].data_ptr(), slot["pre_rng"][0].data_ptr(), sa),
-                  "qa_perm_resolve")
+            # one launch for the chained resolves (#1: stream position only): the cluster keeps its SMs while the
+            # tile-stat kernels flood the rest of the GPU
+            check(L.qa_perm_resolve_chain(self._rng0.data_ptr(), n, 3 if three else 2, 0b110 if three else 0b010,
+                                          slot["jarr"].data_ptr(), slot["rngs"].data_ptr(), sa), "qa_perm_resolve_chain")
+            mark("resolve", side)
             if three:
                 slot["ev"].record(side)
                 side2.wait_event(slot["ev"])
-                check(L.qa_perm_apply(slot["jarr"][0].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
+                check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
                                       slot["apply_work"][0].data_ptr(), side2.cuda_stream), "qa_perm_apply")
-                check(L.qa_perm_resolve(slot["pre_rng"][0].data_ptr(), n, slot["jarr"][1].data_ptr(), slot["pre_rng"][1].data_ptr(), sa),
-                      "qa_perm_resolve")
-                check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][1].data_ptr(),
+                check(L.qa_perm_apply(slot["jarr"][2].data_ptr(), n, None, slot["pre_order"][1].data_ptr(),
                                       slot["apply_work"][1].data_ptr(), sa), "qa_perm_apply")
             else:
-                check(L.qa_perm_apply(slot["jarr"][0].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
+                check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
                                       slot["apply_work"][0].data_ptr(), sa), "qa_perm_apply")
+        if pre:
+            mark("prefetch", side)
         if stats:
+            ss = self.stats_streams[self._stats_rr % len(self.stats_streams)]
+            self._stats_rr += 1
+            ss.wait_stream(stream)                       # the tensor's input is in place (H2D copy / previous pass)
             check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
                                   0xF, STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS,
-                                  slot["table"].data_ptr(), sp), "qa_tile_stats")
+                                  slot["table"].data_ptr(), ss.cuda_stream), "qa_tile_stats")
+            stream.wait_stream(ss)
+            mark("stats")
         if assign:
             slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
             args = (slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
@@ -120,13 +142,15 @@ class GreedyBatch:
                 # initial sums + delta records on the main stream (overlaps the prefetch), then the chain
                 check(L.qa_greedy_init(slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order,
                                        len(self.tile_formats), slot["init"].data_ptr(), sp), "qa_greedy_init")
+                mark("init")
                 if pre:
                     stream.wait_stream(side)
                     if len(self.tile_formats) >= 3:
                         stream.wait_stream(side2)
                 check(L.qa_greedy_assign_par_pre(*args, slot["pre_order"].data_ptr() if pre else None,
-                                                 slot["pre_rng"].data_ptr() if pre else None, slot["init"].data_ptr(), sp),
+                                                 slot["rngs"][1].data_ptr() if pre else None, slot["init"].data_ptr(), sp),
                       "qa_greedy_assign_par_pre")
+            mark("chain")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
                 check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,
                                            slot["sums"].data_ptr(), sp), "qa_assignment_sums")
@@ -158,6 +182,20 @@ class GreedyBatch:
         if (stats, assign) not in self._graphs:
             self.capture(stats, assign)
         self._graphs[(stats, assign)].replay()
+
+    def timeline(self) -> list[dict]:
+        """After an eager run() with ``self.trace = {}``: per tensor, ms from its stream's start mark to each stage's end."""
+        torch.cuda.synchronize(self.device)
+        out = []
+        t0 = min((tr["start"] for tr in self.trace.values()), key=lambda e: 0)     # any start (all follow the same fork)
+        for s in self.slots:
+            tr = self.trace.get(id(s), {})
+            row = {"shape": (s["rows"], s["cols"])}
+            for tag, ev in tr.items():
+                if tag != "start":
+                    row[tag] = t0.elapsed_time(ev)
+            out.append(row)
+        return out
 
     def run_from_host(self, host_tensors) -> list[dict]:
         """End-to-end pass: pinned host bf16 -> device, quantize+score+assign, results back to host."""

@@ -935,6 +935,25 @@ __global__ void __launch_bounds__(GT) perm_resolve_kernel(const qa_pcg64* rng_in
     }
 }
 
+// `count` consecutive permutations of n items from one stream in ONE launch: the cluster keeps its SMs between them
+// (a cluster that has to be re-placed while a streaming kernel floods the GPU waits for that kernel to drain).
+__global__ void __launch_bounds__(GT) perm_resolve_chain_kernel(const qa_pcg64* rng_in, int n, int count, unsigned write_mask,
+                                                                int32_t* jarr, qa_pcg64* rng_out) {
+    __shared__ Sh sh;
+    Coop c(sh);
+    Pcg g;
+    g.load(rng_in);
+    c.sync();
+    for (int k = 0; k < count; ++k) {
+        perm_resolve(c, g, n, ((write_mask >> k) & 1u) ? jarr + (size_t)k * n : nullptr);
+        if (c.gtid == 0) {
+            rng_out[k].inc_hi = g.inc.hi;
+            rng_out[k].inc_lo = g.inc.lo;
+            g.store(rng_out + k);
+        }
+    }
+}
+
 // The first permutations of a greedy run do not depend on the data: the base pass permutes all n tiles (only the
 // stream position matters, the order is irrelevant); unless the base state already fails, pass 2 permutes all n
 // tiles again; and when pass 2 accepts every tile (the usual outcome for the first, nearly lossless candidate
@@ -1637,8 +1656,7 @@ static int pick_cluster(int64_t n) {
 }
 
 template <typename... KArgs, typename... Args>
-static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
-    constexpr int dyn = STAGE_SLOTS * GT * (int)sizeof(double);
+static int launch_cluster_dyn(int dyn, void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
     {   // attributes are set once per kernel (not a stream operation: keep it out of the per-launch path and of graph captures)
         static void* done[32];
         static int ndone = 0;
@@ -1665,13 +1683,24 @@ static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args..
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
     if (e != cudaSuccess && nr > 8) {           // no GPC can host 16 co-resident CTAs right now: portable size
         (void)cudaGetLastError();
-        return launch_cluster(kern, 8, s, args...);
+        return launch_cluster_dyn(dyn, kern, 8, s, args...);
     }
     if (e != cudaSuccess) {
         set_error("cluster launch (%d CTAs): %s", nr, cudaGetErrorString(e));
         return 2;
     }
     return 0;
+}
+
+// kernels that stage addends in dynamic shared memory (init / chain) vs. the ones that do not (permutation resolve:
+// a smaller footprint is easier to place next to a streaming kernel)
+template <typename... KArgs, typename... Args>
+static int launch_cluster(void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
+    return launch_cluster_dyn(STAGE_SLOTS * GT * (int)sizeof(double), kern, nr, s, args...);
+}
+template <typename... KArgs, typename... Args>
+static int launch_cluster_nostage(void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
+    return launch_cluster_dyn(0, kern, nr, s, args...);
 }
 
 }  // namespace qa
@@ -1694,7 +1723,17 @@ extern "C" int qa_numpy_permutation_par(qa_pcg64* rng, int64_t n, int32_t* out_p
 
 extern "C" int qa_perm_resolve(const qa_pcg64* rng_in, int64_t n, int32_t* jarr, qa_pcg64* rng_out, qa_stream_t stream) {
     if (!rng_in || !rng_out || n <= 0 || n > 0x3FFFFFFF) { set_error("qa_perm_resolve: bad args"); return 1; }
-    return launch_cluster(perm_resolve_kernel, pick_cluster(n), (cudaStream_t)stream, rng_in, (int)n, jarr, rng_out);
+    return launch_cluster_nostage(perm_resolve_kernel, pick_cluster(n), (cudaStream_t)stream, rng_in, (int)n, jarr, rng_out);
+}
+
+extern "C" int qa_perm_resolve_chain(const qa_pcg64* rng_in, int64_t n, int count, uint32_t write_mask, int32_t* jarr,
+                                     qa_pcg64* rng_out, qa_stream_t stream) {
+    if (!rng_in || !rng_out || n <= 0 || n > 0x3FFFFFFF || count < 1 || count > 32 || (write_mask && !jarr)) {
+        set_error("qa_perm_resolve_chain: bad args");
+        return 1;
+    }
+    return launch_cluster_nostage(perm_resolve_chain_kernel, pick_cluster(n), (cudaStream_t)stream, rng_in, (int)n, count, (unsigned)write_mask,
+                          jarr, rng_out);
 }
 
 extern "C" int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int nfmt, int32_t* pre_order, qa_pcg64* pre_rng, void* work,
