@@ -151,6 +151,12 @@ int qa_greedy_prefetch(const qa_pcg64* rng, int64_t n, int nfmt, int32_t* pre_or
 int64_t qa_greedy_init_bytes(int64_t ntiles);
 int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
                    void* init, qa_stream_t stream);
+/* The two halves of qa_greedy_init for callers that run them on different streams: the sums (one cluster, latency
+ * bound) and the delta records (a plain grid kernel) write disjoint parts of `init`; the greedy needs both. */
+int qa_greedy_init_sums(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
+                        void* init, qa_stream_t stream);
+int qa_greedy_init_deltas(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
+                          void* init, qa_stream_t stream);
 int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric,
                              double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
                              int8_t* assignment, int64_t* counts, double* state, void* work,

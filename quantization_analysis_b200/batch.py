@@ -71,7 +71,7 @@ class GreedyBatch:
         elif not self.prefetch:
             per_tensor = 3
         else:
-            per_tensor = 3 + (1 + 2 * 7 if len(self.tile_formats) >= 3 else 1 + 7)
+            per_tensor = 4 + (1 + 2 * 7 if len(self.tile_formats) >= 3 else 1 + 7)
         self.launches_per_step = per_tensor * len(self.slots)
 
     # ---- data movement -------------------------------------------------------------------
@@ -140,8 +140,16 @@ class GreedyBatch:
                 check(L.qa_greedy_assign(*args, sp), "qa_greedy_assign")
             else:
                 # initial sums + delta records on the main stream (overlaps the prefetch), then the chain
-                check(L.qa_greedy_init(slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order,
-                                       len(self.tile_formats), slot["init"].data_ptr(), sp), "qa_greedy_init")
+                iargs = (slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order,
+                         len(self.tile_formats), slot["init"].data_ptr())
+                if stats:
+                    # the delta records are a plain grid kernel: on the tile-stat stream right behind this tensor's pass,
+                    # next to the (latency-bound, one-cluster) sums rather than in front of them
+                    check(L.qa_greedy_init_deltas(*iargs, ss.cuda_stream), "qa_greedy_init_deltas")
+                    check(L.qa_greedy_init_sums(*iargs, sp), "qa_greedy_init_sums")
+                    stream.wait_stream(ss)
+                else:
+                    check(L.qa_greedy_init(*iargs, sp), "qa_greedy_init")
                 mark("init")
                 if pre:
                     stream.wait_stream(side)

@@ -84,6 +84,7 @@ struct Sh {
     long long xl[2][MAXR][12];
     double xd[2][MAXR];
     int cnt[QA_NFMT];
+    unsigned tail_draws[256];    // permutation tail: one batch of 32-bit draws
     unsigned long long mbar;     // cluster exchange barrier: one arrival per CTA per exchange
 };
 
@@ -790,29 +791,69 @@ __device__ void perm_resolve(Coop& c, Pcg& g, int m, int32_t* jarr) {     // jar
     __syncthreads();
     const long long t_tail0 = clock64();
 #endif
-    // sequential tail and stream hand-back: computed redundantly (and identically) by one thread per CTA
-    if (tid == 0) {
-        const unsigned long long klast = (pnext - 1ull) >> 1;
-        u128 a2, p2;
-        lcg_jump_consts(g.inc, klast - rk, a2, p2);
-        const u128 s = add128(mul128(a2, rs), p2);
-        Pcg t;
-        t.inc = g.inc;
-        t.s = s;
-        t.has32 = ((pnext - 1ull) & 1ull) == 0ull ? 1u : 0u;   // last consumed draw was a low half
-        t.buf32 = (uint32_t)(pcg_out(s) >> 32);
-        for (int i = i_cur; i >= 1; --i) {
-            const int32_t j = (int32_t)t.interval((uint32_t)i);
-            if (c.rank == 0 && jarr) jarr[i] = j;
+    // tail (the last <= SEQ_TAIL steps) and stream hand-back, by warp 0 of every CTA (redundantly, identically): the
+    // lanes generate the next 256 draws in parallel (one LCG jump per lane), lane 0 consumes them in order.
+    if (tid < 32) {
+        const int lane = tid;
+        unsigned long long pcur = pnext;                      // next unconsumed draw position
+        unsigned long long k0 = pcur >> 1;                    // output index of the batch's first 64-bit draw
+        u128 a2, p2, la, lp, ba, bp;
+        lcg_jump_consts(g.inc, k0 - rk, a2, p2);
+        u128 sb = add128(mul128(a2, rs), p2);                 // state at output index k0
+        lcg_jump_consts(g.inc, 4ull * (uint64_t)lane, la, lp);
+        lcg_jump_consts(g.inc, 128ull, ba, bp);
+        long long* st = c.sh.i64;                             // [128][2] LCG states of the batch
+        unsigned* dr = c.sh.tail_draws;                       // [256] 32-bit draws of the batch, in stream order
+        int i = i_cur;
+        for (;;) {
+            u128 sl = add128(mul128(la, sb), lp);             // state at k0 + 4 * lane
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint64_t o = pcg_out(sl);
+                const int idx = 4 * lane + q;
+                dr[2 * idx] = (uint32_t)o;
+                dr[2 * idx + 1] = (uint32_t)(o >> 32);
+                st[2 * idx] = (long long)sl.hi;
+                st[2 * idx + 1] = (long long)sl.lo;
+                sl = pcg_step(sl, g.inc);
+            }
+            __syncwarp();
+            int used = 0;
+            if (lane == 0) {
+                int off = (int)(pcur - 2ull * k0);            // 1 if the batch's first low half was consumed earlier
+                while (i >= 1 && off < 256) {
+                    const uint32_t mask = 0xFFFFFFFFu >> __clz((uint32_t)i);
+                    const uint32_t v = dr[off++] & mask;
+                    if (v <= (uint32_t)i) {
+                        if (c.rank == 0 && jarr) jarr[i] = (int32_t)v;
+                        --i;
+                    }
+                }
+                used = off;
+            }
+            used = __shfl_sync(0xFFFFFFFFu, used, 0);
+            i = __shfl_sync(0xFFFFFFFFu, i, 0);
+            pcur = 2ull * k0 + (unsigned long long)used;
+            if (i < 1) break;
+            __syncwarp();
+            k0 += 128ull;
+            sb = add128(mul128(ba, sb), bp);
+            pcur = 2ull * k0;
         }
-        c.sh.i64[0] = (long long)t.s.hi;
-        c.sh.i64[1] = (long long)t.s.lo;
-        c.sh.i32[3 * NW + 2] = (int)t.has32;
-        c.sh.i32[3 * NW + 3] = (int)t.buf32;
+        if (lane == 0) {
+            const unsigned long long pl = pcur - 1ull;        // last consumed draw (the tail always consumes one)
+            const int idx = (int)((pl >> 1) - k0);
+            const long long shi = st[2 * idx], slo = st[2 * idx + 1];
+            const unsigned hi_half = dr[2 * idx + 1];
+            c.sh.i32[3 * NW + 2] = (pl & 1ull) == 0ull ? 1 : 0;     // a low half was consumed last: its high half is buffered
+            c.sh.i32[3 * NW + 3] = (int)hi_half;
+            c.sh.i64[256] = shi;
+            c.sh.i64[257] = slo;
+        }
     }
     __syncthreads();
-    g.s.hi = (uint64_t)c.sh.i64[0];
-    g.s.lo = (uint64_t)c.sh.i64[1];
+    g.s.hi = (uint64_t)c.sh.i64[256];
+    g.s.lo = (uint64_t)c.sh.i64[257];
     g.has32 = (uint32_t)c.sh.i32[3 * NW + 2];
     g.buf32 = (uint32_t)c.sh.i32[3 * NW + 3];
     c.sync();
@@ -1130,7 +1171,8 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
 // hdr: [0] sx  [1] sx2  [2..5] sy, sy2, sxy, sabs of the base format  [6] degraded bits  [7] cycles
 //      [8] cycles of the non-negative columns  [9] cycles of the signed columns  [10] scan rounds
 template <bool PCC>
-__device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, const ParOrder& ord, double* hdr, double* delta) {
+__device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, const ParOrder& ord, double* hdr, double* delta,
+                           bool build_deltas) {
     const int base = ord.fmt[0];
     const long long t_start = clock64();
     double sx = 0.0, sx2 = 0.0;
@@ -1180,20 +1222,33 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
     double dr[QA_NFMT - 1];                      // per transition: sum |delta sy| over all tiles (bounds the drift of sy)
 #pragma unroll
     for (int tr = 0; tr + 1 < QA_NFMT; ++tr) dr[tr] = 0.0;
-    for (int t = c.gtid; t < nt; t += c.gth) {
-        double v[QA_NFMT][4];
+    if (build_deltas) {
+        for (int t = c.gtid; t < nt; t += c.gth) {
+            double v[QA_NFMT][4];
 #pragma unroll
-        for (int f = 0; f < QA_NFMT; ++f)
+            for (int f = 0; f < QA_NFMT; ++f)
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[f][q] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], q) * nt + t] : 0.0;
+                for (int q = 0; q < 4; ++q) v[f][q] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], q) * nt + t] : 0.0;
 #pragma unroll
-        for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
-            if (tr + 1 >= ord.n) break;
-            double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
-            const double d0 = __dsub_rn(v[tr + 1][0], v[tr][0]);
-            dr[tr] += fabs(d0);
-            dst[0] = make_double2(d0, __dsub_rn(v[tr + 1][1], v[tr][1]));
-            dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
+            for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
+                if (tr + 1 >= ord.n) break;
+                double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
+                const double d0 = __dsub_rn(v[tr + 1][0], v[tr][0]);
+                dr[tr] += fabs(d0);
+                dst[0] = make_double2(d0, __dsub_rn(v[tr + 1][1], v[tr][1]));
+                dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
+            }
+        }
+    } else if (PCC) {
+        // the records are written by greedy_delta_kernel next to this kernel; only the drift bounds are needed here
+        // (same terms, same order as above)
+        for (int t = c.gtid; t < nt; t += c.gth) {
+            double v[QA_NFMT];
+#pragma unroll
+            for (int f = 0; f < QA_NFMT; ++f) v[f] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], 0) * nt + t] : 0.0;
+#pragma unroll
+            for (int tr = 0; tr + 1 < QA_NFMT; ++tr)
+                if (tr + 1 < ord.n) dr[tr] += fabs(__dsub_rn(v[tr + 1], v[tr]));
         }
     }
 #pragma unroll
@@ -1214,7 +1269,25 @@ __global__ void __launch_bounds__(GT) greedy_init_kernel(const double* __restric
                                                          double* delta) {
     __shared__ Sh sh;
     Coop c(sh);
-    init_phase<PCC>(c, table, nt, ord, hdr, delta);
+    init_phase<PCC>(c, table, nt, ord, hdr, delta, delta != nullptr);
+}
+
+// delta records of every format transition, one thread per tile (the grid-kernel half of qa_greedy_init)
+__global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restrict__ table, int nt, ParOrder ord, double* delta) {
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= nt) return;
+    double v[QA_NFMT][4];
+#pragma unroll
+    for (int f = 0; f < QA_NFMT; ++f)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[f][q] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], q) * nt + t] : 0.0;
+#pragma unroll
+    for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
+        if (tr + 1 >= ord.n) break;
+        double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
+        dst[0] = make_double2(__dsub_rn(v[tr + 1][0], v[tr][0]), __dsub_rn(v[tr + 1][1], v[tr][1]));
+        dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1244,7 +1317,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
 
     // ---- (1) initial sums, sequentially rounded in tile order (greedy_init_kernel ran ahead, or inline) ----
     if (!have_init) {
-        init_phase<PCC>(c, table, nt, ord, w.hdr, w.delta);
+        init_phase<PCC>(c, table, nt, ord, w.hdr, w.delta, true);
         c.sync();
     }
     Consts k;
@@ -1755,17 +1828,39 @@ static int fill_order(const int32_t* fmt_order, int nfmt, ParOrder& ord, const c
     return 0;
 }
 
-extern "C" int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
-                              qa_stream_t stream) {
-    if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !init) { set_error("qa_greedy_init: bad args"); return 1; }
-    if (metric != QA_METRIC_PCC && metric != QA_METRIC_MAE) { set_error("qa_greedy_init: metric must be pcc or mae"); return 1; }
+static int greedy_init_launch(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
+                              bool sums, bool deltas, bool deltas_in_cluster, qa_stream_t stream, const char* who) {
+    if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !init) { set_error("%s: bad args", who); return 1; }
+    if (metric != QA_METRIC_PCC && metric != QA_METRIC_MAE) { set_error("%s: metric must be pcc or mae", who); return 1; }
     ParOrder ord;
-    if (fill_order(fmt_order, nfmt, ord, "qa_greedy_init")) return 1;
+    if (fill_order(fmt_order, nfmt, ord, who)) return 1;
     double* hdr = reinterpret_cast<double*>(init);
     double* delta = reinterpret_cast<double*>(reinterpret_cast<char*>(init) + al(8 * HDR_DOUBLES));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (deltas && !deltas_in_cluster) {
+        greedy_delta_kernel<<<(unsigned)cdiv(ntiles, 256), 256, 0, s>>>(table, (int)ntiles, ord, delta);
+        if (int rc = check_launch(who)) return rc;
+    }
+    if (!sums) return 0;
+    double* dcl = deltas_in_cluster ? delta : nullptr;
     if (metric == QA_METRIC_PCC)
-        return launch_cluster(greedy_init_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, ord, hdr, delta);
-    return launch_cluster(greedy_init_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, ord, hdr, delta);
+        return launch_cluster(greedy_init_kernel<true>, pick_cluster(ntiles), s, table, (int)ntiles, ord, hdr, dcl);
+    return launch_cluster(greedy_init_kernel<false>, pick_cluster(ntiles), s, table, (int)ntiles, ord, hdr, dcl);
+}
+
+extern "C" int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
+                              qa_stream_t stream) {
+    return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, true, true, false, stream, "qa_greedy_init");
+}
+
+extern "C" int qa_greedy_init_sums(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
+                                   qa_stream_t stream) {
+    return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, true, false, false, stream, "qa_greedy_init_sums");
+}
+
+extern "C" int qa_greedy_init_deltas(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
+                                     qa_stream_t stream) {
+    return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, false, true, false, stream, "qa_greedy_init_deltas");
 }
 
 extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
