@@ -78,6 +78,12 @@ int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_
                   int64_t vec_tail, uint32_t fmt_mask, int mode, double* table,
                   qa_stream_t stream);
 
+/* qa_tile_stats (fast modes, bf16) restricted to tile rows [tile_row_begin, tile_row_end) of the same table: a large
+ * tensor's table can be produced in pieces so that consumers of its first tiles (qa_greedy_init_sums_range) start early. */
+int qa_tile_stats_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                       uint32_t fmt_mask, int mode, double* table, int64_t tile_row_begin,
+                       int64_t tile_row_end, qa_stream_t stream);
+
 /* NumPy-float32-faithful per-tile scores on zero-padded 32x32 tiles.
  * Replaces tile_utils.py:46-57 (tile_metrics) incl. metrics.py:6-16 (pearson_corr) with the
  * float32 summation orders of NumPy 2.3.5 / OpenBLAS 0.3.30 SkylakeX.
@@ -155,13 +161,31 @@ int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_
  * bound) and the delta records (a plain grid kernel) write disjoint parts of `init`; the greedy needs both. */
 int qa_greedy_init_sums(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
                         void* init, qa_stream_t stream);
+/* qa_greedy_init_sums over tiles [tile_begin, tile_end) in order: calls must cover [0, ntiles) consecutively on the same
+ * `init`; only the call that reaches ntiles needs the whole table (the earlier ones read tiles < tile_end). */
+int qa_greedy_init_sums_range(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order,
+                              int nfmt, void* init, int64_t tile_begin, int64_t tile_end,
+                              qa_stream_t stream);
 int qa_greedy_init_deltas(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
                           void* init, qa_stream_t stream);
+/* qa_greedy_assign_par_pre restricted to passes [pass_begin, pass_end) of the format order (pass 0 = base format).
+ * Consecutive calls covering [0, nfmt) on the same buffers give the results of the single call; the running state
+ * travels in `work`.  Lets a caller start the early passes before the speculative third permutation is ready. */
+int qa_greedy_assign_passes(const double* table, int64_t ntiles, double numel, int metric,
+                            double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
+                            int8_t* assignment, int64_t* counts, double* state, void* work,
+                            const int32_t* pre_order, const qa_pcg64* pre_rng, const void* init,
+                            int pass_begin, int pass_end, qa_stream_t stream);
 int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric,
                              double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
                              int8_t* assignment, int64_t* counts, double* state, void* work,
                              const int32_t* pre_order, const qa_pcg64* pre_rng, const void* init,
                              qa_stream_t stream);
+
+/* Diagnostic timeline: device timestamps (ns) {first start, last end} of the cluster kernels since the last reset -
+ * resolve chain, init sums, chain launch containing pass 0, later chain launch - one row of 8 per cluster-size class
+ * (log2 of the cluster size, 0..4).  out8_host: HOST array of 40 (may be NULL); reset != 0 re-arms the slots.  Synchronous (cudaMemcpy{From,To}Symbol). */
+int qa_debug_times(unsigned long long* out8_host, int reset);
 
 /* Diagnostic: cycles per call of the cluster collectives used by qa_greedy_assign_par
  * (out double[8] on device: scan+flag exchange, 3-way min, cluster.sync, __syncthreads, pair scan). */

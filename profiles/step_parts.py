@@ -46,6 +46,15 @@ def chain(st):
                                      st.cuda_stream), "chain")
 
 
+def chain_passes(st, b0, e0):
+    if b0 == 0:
+        s["rng"].copy_(b._rng0, non_blocking=True)
+    check(L.qa_greedy_assign_passes(s["table"].data_ptr(), n, float(s["numel"]), METRIC_CODE["pcc"], 0.999, b._order, 4,
+                                    s["rng"].data_ptr(), s["assignment"].data_ptr(), s["counts"].data_ptr(), s["state"].data_ptr(),
+                                    s["work"].data_ptr(), s["pre_order"].data_ptr(), s["rngs"][1].data_ptr(), s["init"].data_ptr(),
+                                    b0, e0, st.cuda_stream), "chain passes")
+
+
 def timed(fn, reps=20):
     g = torch.cuda.CUDAGraph()
     fn(torch.cuda.current_stream()); torch.cuda.synchronize()
@@ -85,6 +94,8 @@ print(f"resolve x1           {timed(lambda st: resolves(st, 1)):7.1f} us")
 print(f"resolve x3           {timed(lambda st: resolves(st, 3)):7.1f} us")
 print(f"apply x1             {timed(lambda st: apply(st, 0)):7.1f} us")
 print(f"chain                {timed(chain):7.1f} us")
+print(f"chain passes 0-1     {timed(lambda st: chain_passes(st, 0, 2)):7.1f} us")
+print(f"chain passes 0-1, 2-3 {timed(lambda st: (chain_passes(st, 0, 2), chain_passes(st, 2, 4))):7.1f} us")
 print(f"init -> chain        {timed(lambda st: (init(st), chain(st))):7.1f} us")
 print(f"stats->init->chain   {timed(lambda st: (stats(st), init(st), chain(st))):7.1f} us")
 print(f"prefetch | init -> chain   {timed(lambda st: full(st, with_stats=False)):7.1f} us")

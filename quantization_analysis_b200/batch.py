@@ -17,6 +17,9 @@ MIXED = engine.MIXED_FORMATS
 
 
 class GreedyBatch:
+    PIPELINE_MIN_TILES = 65536      # tensors at least this large produce their table in two pieces (see _enqueue)
+    PIPELINE_FIRST_TILES = 16384    # ... the first of about this many tiles
+
     def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
                  tile_formats=MIXED, n_streams: int | None = None, device=None):
         self.device = device or engine._require_cuda()
@@ -29,7 +32,7 @@ class GreedyBatch:
         # kernels on normal-priority ones, so the block scheduler drains SMs for a pending cluster first.
         self.streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(1, n_streams))]
         self.side_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(1, n_streams))]
-        self.side2_streams = [torch.cuda.Stream(device=self.device) for _ in range(max(1, n_streams))]
+        self.side2_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(max(1, n_streams))]
         # The tile-stat kernels are bandwidth-bound and each fills the GPU: run concurrently they only slow each other
         # down, and the largest tensor - whose init/chain is the critical path - would get its table last.  A short
         # list of large tensors therefore streams its tile-stat passes one after the other, largest first; a long list
@@ -59,20 +62,27 @@ class GreedyBatch:
                 "jarr": torch.empty((3, nt), dtype=torch.int32, device=self.device),
                 "apply_work": torch.empty((2, L.qa_perm_apply_work_bytes(nt)), dtype=torch.uint8, device=self.device),
                 "ev": torch.cuda.Event(),
+                "ev2": torch.cuda.Event(),
+                "ev3": torch.cuda.Event(),
             })
         self._rng0 = rng0
         self._graphs = {}
         self.trace = None            # set to {} to record per-tensor stage events during eager run() (see timeline())
         self._order = _lib.int32_array([engine.FMT_INDEX[f] for f in self.tile_formats])
-        # kernels of ours per tensor and step.  atol: tile_stats + greedy + assignment_sums.  pcc / mae: tile_stats +
-        # greedy_init + greedy chain, plus the prefetched permutations (one chained resolve kernel, 7 grid kernels per apply)
-        if metric == "atol":
-            per_tensor = 3
-        elif not self.prefetch:
-            per_tensor = 3
-        else:
-            per_tensor = 4 + (1 + 2 * 7 if len(self.tile_formats) >= 3 else 1 + 7)
-        self.launches_per_step = per_tensor * len(self.slots)
+        # kernels of ours per tensor and step.  atol: tile_stats + greedy + assignment_sums.  pcc / mae: tile_stats,
+        # init sums, init deltas, the chain (two launches with three or more formats) and the prefetched permutations (one
+        # chained resolve kernel, 7 grid kernels per apply); a pipelined large tensor adds two tile_stats and two init launches
+        self.launches_per_step = 0
+        for s in self.slots:
+            if metric == "atol":
+                n = 3
+            elif not self.prefetch:
+                n = 4
+            else:
+                n = (5 + 2 + 2 * 7) if len(self.tile_formats) >= 3 else (4 + 1 + 7)
+            if metric != "atol" and s["ntiles"] >= self.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8:
+                n += 4
+            self.launches_per_step += n
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
@@ -104,16 +114,25 @@ class GreedyBatch:
             n, three = slot["ntiles"], len(self.tile_formats) >= 3
             side.wait_stream(stream)
             sa = side.cuda_stream
-            # one launch for the chained resolves (#1: stream position only): the cluster keeps its SMs while the
-            # tile-stat kernels flood the rest of the GPU
-            check(L.qa_perm_resolve_chain(self._rng0.data_ptr(), n, 3 if three else 2, 0b110 if three else 0b010,
-                                          slot["jarr"].data_ptr(), slot["rngs"].data_ptr(), sa), "qa_perm_resolve_chain")
+            if three:
+                # every tensor restarts the seeded stream: a 40-byte copy node, kept off the stats -> init -> chain path
+                # (side2 is idle until the second resolve is done; the chain joins it before its first launch)
+                side2.wait_stream(stream)
+                with torch.cuda.stream(side2):
+                    slot["rng"].copy_(self._rng0, non_blocking=True)
+            # resolves #1 (stream position only) and #2 in one launch: the cluster keeps its SMs while the tile-stat
+            # kernels flood the rest of the GPU.  #3 is a second launch so that #2's apply - all the first chain launch
+            # needs - can start as soon as #2 is resolved; #3 has until the later passes start.
+            check(L.qa_perm_resolve_chain(self._rng0.data_ptr(), n, 2, 0b10, slot["jarr"].data_ptr(), slot["rngs"].data_ptr(), sa),
+                  "qa_perm_resolve_chain")
             mark("resolve", side)
             if three:
                 slot["ev"].record(side)
                 side2.wait_event(slot["ev"])
                 check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
                                       slot["apply_work"][0].data_ptr(), side2.cuda_stream), "qa_perm_apply")
+                check(L.qa_perm_resolve(slot["rngs"][1].data_ptr(), n, slot["jarr"][2].data_ptr(), slot["rngs"][2].data_ptr(), sa),
+                      "qa_perm_resolve")
                 check(L.qa_perm_apply(slot["jarr"][2].data_ptr(), n, None, slot["pre_order"][1].data_ptr(),
                                       slot["apply_work"][1].data_ptr(), sa), "qa_perm_apply")
             else:
@@ -121,17 +140,41 @@ class GreedyBatch:
                                       slot["apply_work"][0].data_ptr(), sa), "qa_perm_apply")
         if pre:
             mark("prefetch", side)
+        mode = STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS
+        iargs = (slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order, len(self.tile_formats),
+                 slot["init"].data_ptr())
+        split = 0            # tile rows in the first piece of a pipelined table (0: one piece)
         if stats:
             ss = self.stats_streams[self._stats_rr % len(self.stats_streams)]
             self._stats_rr += 1
             ss.wait_stream(stream)                       # the tensor's input is in place (H2D copy / previous pass)
-            check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
-                                  0xF, STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS,
-                                  slot["table"].data_ptr(), ss.cuda_stream), "qa_tile_stats")
+            tiles_h, tiles_w = -(-slot["rows"] // 32), -(-slot["cols"] // 32)
+            if assign and self.metric != "atol" and slot["ntiles"] >= self.PIPELINE_MIN_TILES and tiles_h >= 8:
+                # Large tensor: the sequential initial sums spend most of their rounds on the first few thousand tiles
+                # (the running sums double often while they are small).  Produce the table in two pieces and let the
+                # sums over the first piece run while the tile-stat pass streams the rest of the tensor.
+                split = max(1, min(tiles_h - 2, -(-self.PIPELINE_FIRST_TILES // tiles_w)))
+                split2 = max(split + 1, tiles_h // 2)                      # second cut: half of the tensor
+                sargs = (slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0xF, mode,
+                         slot["table"].data_ptr())
+                check(L.qa_tile_stats_rows(*sargs, 0, split, ss.cuda_stream), "qa_tile_stats_rows")
+                slot["ev2"].record(ss)
+                check(L.qa_tile_stats_rows(*sargs, split, split2, ss.cuda_stream), "qa_tile_stats_rows")
+                slot["ev3"].record(ss)
+                check(L.qa_tile_stats_rows(*sargs, split2, tiles_h, ss.cuda_stream), "qa_tile_stats_rows")
+                stream.wait_event(slot["ev2"])
+                check(L.qa_greedy_init_sums_range(*iargs, 0, split * tiles_w, sp), "qa_greedy_init_sums_range")
+                stream.wait_event(slot["ev3"])
+                check(L.qa_greedy_init_sums_range(*iargs, split * tiles_w, split2 * tiles_w, sp), "qa_greedy_init_sums_range")
+                split = split2
+            else:
+                check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
+                                      0xF, mode, slot["table"].data_ptr(), ss.cuda_stream), "qa_tile_stats")
             stream.wait_stream(ss)
             mark("stats")
         if assign:
-            slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
+            if not (pre and len(self.tile_formats) >= 3):
+                slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
             args = (slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
                     METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
                     slot["rng"].data_ptr(), slot["assignment"].data_ptr(), slot["counts"].data_ptr(),
@@ -140,24 +183,30 @@ class GreedyBatch:
                 check(L.qa_greedy_assign(*args, sp), "qa_greedy_assign")
             else:
                 # initial sums + delta records on the main stream (overlaps the prefetch), then the chain
-                iargs = (slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order,
-                         len(self.tile_formats), slot["init"].data_ptr())
                 if stats:
                     # the delta records are a plain grid kernel: on the tile-stat stream right behind this tensor's pass,
                     # next to the (latency-bound, one-cluster) sums rather than in front of them
                     check(L.qa_greedy_init_deltas(*iargs, ss.cuda_stream), "qa_greedy_init_deltas")
-                    check(L.qa_greedy_init_sums(*iargs, sp), "qa_greedy_init_sums")
+                    tiles_w = -(-slot["cols"] // 32)
+                    check(L.qa_greedy_init_sums_range(*iargs, split * tiles_w, slot["ntiles"], sp), "qa_greedy_init_sums_range")
                     stream.wait_stream(ss)
                 else:
                     check(L.qa_greedy_init(*iargs, sp), "qa_greedy_init")
                 mark("init")
-                if pre:
+                pargs = args + (slot["pre_order"].data_ptr() if pre else None, slot["rngs"][1].data_ptr() if pre else None,
+                                slot["init"].data_ptr())
+                nf = len(self.tile_formats)
+                if pre and nf >= 3:
+                    # passes 0-1 only need permutation #2 (applied on side2 while #3 is still being drawn); the later
+                    # passes wait for the speculative #3 (applied last on the side stream)
+                    stream.wait_stream(side2)
+                    check(L.qa_greedy_assign_passes(*pargs, 0, 2, sp), "qa_greedy_assign_passes")
                     stream.wait_stream(side)
-                    if len(self.tile_formats) >= 3:
-                        stream.wait_stream(side2)
-                check(L.qa_greedy_assign_par_pre(*args, slot["pre_order"].data_ptr() if pre else None,
-                                                 slot["rngs"][1].data_ptr() if pre else None, slot["init"].data_ptr(), sp),
-                      "qa_greedy_assign_par_pre")
+                    check(L.qa_greedy_assign_passes(*pargs, 2, nf, sp), "qa_greedy_assign_passes")
+                else:
+                    if pre:
+                        stream.wait_stream(side)
+                    check(L.qa_greedy_assign_passes(*pargs, 0, nf, sp), "qa_greedy_assign_passes")
             mark("chain")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
                 check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,

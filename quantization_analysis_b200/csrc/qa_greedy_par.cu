@@ -43,6 +43,20 @@ constexpr int EPS = 8;           // elements each thread streams through per chu
 constexpr int SEQ_TAIL = 96;      // last Fisher-Yates steps are drawn by one thread
 constexpr long long M_LO = 1ll << 52, M_HI = 1ll << 53;
 
+// Diagnostic timeline: first-start / last-end device timestamps (ns, %globaltimer) of the cluster kernels of this file,
+// read back with qa_debug_times.  Slots: 0/1 resolve chain, 2/3 init sums, 4/5 chain launch with pass 0, 6/7 later launch.
+// One row of 8 per cluster-size class (log2 of the cluster size, 0..4), so tensors of different sizes can be told apart.
+__device__ unsigned long long qa_times[5 * 8];
+__device__ __forceinline__ void stamp(int slot, bool is_end) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned nr;
+    asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(nr));
+    const int cls = 31 - __clz((int)(nr | 1u));
+    if (is_end) atomicMax(&qa_times[cls * 8 + slot], t);
+    else atomicMin(&qa_times[cls * 8 + slot], t);
+}
+
 struct ParOrder {
     int32_t fmt[QA_NFMT];
     int n;
@@ -58,6 +72,7 @@ struct ParWork {
     int32_t* succ;    // [n]
     int32_t* parent;  // [n]
     double* hdr;      // [32]    initial sums + diagnostics (greedy_init_kernel or the inline init phase)
+    double* res;      // [32]    running state handed from one launch of the chain to the next (pass ranges)
     double* delta;    // [3][n][4] per-tile deltas {sy, sy2, sxy, sabs} of the format transitions, tile order
     uint8_t* fixed;   // [n]
     const int32_t* pre_order;   // optional: permutations #2 (and #3) of n items, drawn ahead by greedy_prefetch_kernel
@@ -984,6 +999,7 @@ __global__ void __launch_bounds__(GT) perm_resolve_chain_kernel(const qa_pcg64* 
     Coop c(sh);
     Pcg g;
     g.load(rng_in);
+    if (c.gtid == 0) stamp(0, false);
     c.sync();
     for (int k = 0; k < count; ++k) {
         perm_resolve(c, g, n, ((write_mask >> k) & 1u) ? jarr + (size_t)k * n : nullptr);
@@ -993,6 +1009,7 @@ __global__ void __launch_bounds__(GT) perm_resolve_chain_kernel(const qa_pcg64* 
             g.store(rng_out + k);
         }
     }
+    if (c.gtid == 0) stamp(1, true);
 }
 
 // The first permutations of a greedy run do not depend on the data: the base pass permutes all n tiles (only the
@@ -1033,17 +1050,22 @@ __device__ __forceinline__ double& staged(int stream, int j) { return qa_stage[(
 // by one thread; the rest rides the scan.  A column whose running sum keeps leaving its binade (a
 // zero-mean random walk) is finished with a plain tree sum after max_events cuts and flagged.
 template <int NC>
-__device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int nt, double (&S)[NC], unsigned& degraded,
-                                   int max_events) {
+__device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int pos_begin, int nt, double (&S)[NC],
+                                   unsigned& degraded, int max_events) {
+    // elements [pos_begin, nt) in order; pos_begin > 0 continues from the sums in S (the table may be produced in pieces)
     Sh& sh = c.sh;
     const int tid = threadIdx.x;
     constexpr int HEAD = 192;
     static_assert(HEAD <= GT, "head is staged by one CTA pass");
     int events[NC];
 #pragma unroll
-    for (int s = 0; s < NC; ++s) { S[s] = 0.0; events[s] = 0; }
+    for (int s = 0; s < NC; ++s) events[s] = 0;
     degraded = 0;
-    int pos = min(nt, HEAD);
+    int pos = pos_begin;
+    if (pos_begin == 0) {
+#pragma unroll
+    for (int s = 0; s < NC; ++s) S[s] = 0.0;
+    pos = min(nt, HEAD);
     {   // stage the head in shared memory (parallel loads), then one thread per column adds it up in order
         static_assert(NC * HEAD <= STAGE_SLOTS * GT, "head staging does not fit");
         __syncthreads();
@@ -1061,6 +1083,7 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
 #pragma unroll
     for (int s = 0; s < NC; ++s) S[s] = sh.f64[s];
     __syncthreads();
+    }
     const int CHc = c.gth * EPS;
     while (pos < nt) {
         ++c.n_init_rounds;
@@ -1172,7 +1195,10 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
 //      [8] cycles of the non-negative columns  [9] cycles of the signed columns  [10] scan rounds
 template <bool PCC>
 __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, const ParOrder& ord, double* hdr, double* delta,
-                           bool build_deltas) {
+                           bool build_deltas, int t_begin, int t_end) {
+    // Tiles [t_begin, t_end) of the sequential sums; a call with t_end < nt only advances the sums of the non-negative
+    // columns (kept in hdr[16..19]) so that it can run while the rest of the table is still being produced; the call that
+    // reaches nt finishes everything else.
     const int base = ord.fmt[0];
     const long long t_start = clock64();
     double sx = 0.0, sx2 = 0.0;
@@ -1182,11 +1208,15 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
         {   // sums of non-negative terms: few binade changes, always carried faithfully
             const double* const cols[4] = {table + (size_t)QA_STAT_SX2 * nt, table + (size_t)QA_STAT_FMT(base, 1) * nt,
                                            table + (size_t)QA_STAT_FMT(base, 2) * nt, table + (size_t)QA_STAT_FMT(base, 3) * nt};
-            double R[4];
+            double R[4] = {hdr[16], hdr[17], hdr[18], hdr[19]};      // only read when t_begin > 0
             unsigned dg;
             const long long ti = clock64();
-            faithful_init_sums<4>(c, cols, nt, R, dg, 1 << 30);
+            faithful_init_sums<4>(c, cols, t_begin, t_end, R, dg, 1 << 30);
             c.cy_i0 += clock64() - ti;
+            if (t_end < nt) {
+                if (c.gtid == 0) { hdr[16] = R[0]; hdr[17] = R[1]; hdr[18] = R[2]; hdr[19] = R[3]; hdr[20] = (double)c.n_init_rounds; }
+                return;
+            }
             sx2 = R[0]; S[1] = R[1]; S[2] = R[2]; S[3] = R[3];
         }
         {   // signed sums (means).  A sum with heavy cancellation (|sum t| << sum |t|: zero-mean weights) is a
@@ -1206,15 +1236,19 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
                 walk[q] = fabs(R[q]) < 0.25 * sa;
             }
             if (walk[0] && walk[1]) degraded = 3u;
-            else faithful_init_sums<2>(c, cols, nt, R, degraded, 24);
+            else faithful_init_sums<2>(c, cols, 0, nt, R, degraded, 24);
             c.cy_i1 += clock64() - ti;
             sx = R[0]; S[0] = R[1];
         }
     } else {
         const double* const cols[1] = {table + (size_t)QA_STAT_FMT(base, 3) * nt};
-        double R[1];
+        double R[1] = {hdr[16]};
         unsigned dg;
-        faithful_init_sums<1>(c, cols, nt, R, dg, 1 << 30);
+        faithful_init_sums<1>(c, cols, t_begin, t_end, R, dg, 1 << 30);
+        if (t_end < nt) {
+            if (c.gtid == 0) { hdr[16] = R[0]; hdr[20] = (double)c.n_init_rounds; }
+            return;
+        }
         S[3] = R[0];
     }
     // delta[tr][t] = stats(fmt[tr+1]) - stats(fmt[tr]) of tile t: one 32-byte record per tile and transition, so the
@@ -1260,16 +1294,18 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
         hdr[0] = sx; hdr[1] = sx2; hdr[2] = S[0]; hdr[3] = S[1]; hdr[4] = S[2]; hdr[5] = S[3];
         hdr[6] = (double)degraded;
         hdr[7] = (double)(clock64() - t_start);
-        hdr[8] = (double)c.cy_i0; hdr[9] = (double)c.cy_i1; hdr[10] = (double)c.n_init_rounds;
+        hdr[8] = (double)c.cy_i0; hdr[9] = (double)c.cy_i1; hdr[10] = (double)c.n_init_rounds + (t_begin > 0 ? hdr[20] : 0.0);
     }
 }
 
 template <bool PCC>
 __global__ void __launch_bounds__(GT) greedy_init_kernel(const double* __restrict__ table, int nt, ParOrder ord, double* hdr,
-                                                         double* delta) {
+                                                         double* delta, int t_begin, int t_end) {
     __shared__ Sh sh;
     Coop c(sh);
-    init_phase<PCC>(c, table, nt, ord, hdr, delta, delta != nullptr);
+    if (c.gtid == 0) stamp(2, false);
+    init_phase<PCC>(c, table, nt, ord, hdr, delta, delta != nullptr, t_begin, t_end);
+    if (c.gtid == 0) stamp(3, true);
 }
 
 // delta records of every format transition, one thread per tile (the grid-kernel half of qa_greedy_init)
@@ -1296,28 +1332,35 @@ __global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restr
 template <bool PCC>
 __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
-                                                        int64_t* counts, double* state, ParWork w, int have_init) {
+                                                        int64_t* counts, double* state, ParWork w, int have_init, int fi_begin,
+                                                        int fi_end) {
+    // Passes [fi_begin, fi_end) of the format order.  A run may be split into several launches (so that a later pass can
+    // wait for a prefetched permutation that an earlier one does not need); the running state travels in w.res.
     __shared__ Sh sh;
     Coop c(sh);
     const int tid = threadIdx.x;
     const int base = ord.fmt[0];
+    const bool first = fi_begin == 0, last = fi_end >= ord.n;
+    if (c.gtid == 0) stamp(first ? 4 : 6, false);
     constexpr bool is_pcc = PCC;
     // running sums carried with the reference's exact rounding sequence: sy, sy2, sxy (pcc) | sabs (mae).
     // In pcc mode sum|x-y| only enters the degenerate den == 0 branch (mixed_tile_greedy.py:187-188): it is
     // tracked as a plain per-chunk sum (it starts at 0 and would change binade ~40 times on its way up).
     constexpr int NS = PCC ? 3 : 1;
     constexpr int S0 = PCC ? 0 : 3;       // first table statistic among them
-    for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
+    if (first) {
+        for (int t = c.gtid; t < nt; t += c.gth) { assignment[t] = (int8_t)base; w.fixed[t] = 0; }
+        if (c.gtid < QA_NFMT) counts[c.gtid] = c.gtid == base ? nt : 0;
+    }
     if (tid < QA_NFMT) sh.cnt[tid] = 0;
-    if (c.gtid < QA_NFMT) counts[c.gtid] = c.gtid == base ? nt : 0;
     Pcg g;
     g.load(rng);
     c.sync();
     const long long t_start = clock64();
 
     // ---- (1) initial sums, sequentially rounded in tile order (greedy_init_kernel ran ahead, or inline) ----
-    if (!have_init) {
-        init_phase<PCC>(c, table, nt, ord, w.hdr, w.delta, true);
+    if (first && !have_init) {
+        init_phase<PCC>(c, table, nt, ord, w.hdr, w.delta, true, 0, nt);
         c.sync();
     }
     Consts k;
@@ -1333,10 +1376,18 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
     unsigned n_chunks = 0, n_cutshort = 0;
     const long long cyc_init = have_init ? (long long)w.hdr[7] : t_mark - t_start;
     const int CHc = c.gth * EPS;
-    bool base_failed = false, all_tiles_candidates = true;
+    bool base_failed = false, all_tiles_candidates = true, done = false;
     int accepted_last = nt;
+    if (!first) {
+        const double* r = w.res;
+        S[0] = r[0]; S[1] = r[1]; S[2] = r[2]; S[3] = r[3];
+        degraded = (unsigned)r[4]; chain_rounds = (unsigned)r[5];
+        base_failed = r[6] != 0.0; all_tiles_candidates = r[7] != 0.0; accepted_last = (int)r[8];
+        cyc_perm = (long long)r[9]; cyc_chain = (long long)r[10]; done = r[11] != 0.0;
+        n_chunks = (unsigned)r[12]; n_cutshort = (unsigned)r[13];
+    }
 
-    for (int fi = 0; fi < ord.n; ++fi) {
+    for (int fi = fi_begin; fi < fi_end && fi < ord.n && !done; ++fi) {
         const int fmt = ord.fmt[fi];
         // ---- candidates = not-fixed tiles in ascending order ------------------------------
         // The base pass fixes every tile or none, and a pass that accepted all of its candidates fixes none: as long
@@ -1372,6 +1423,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         if (m == 0) {
             // the base pass fixed every tile: only permutation #1 was consumed (rare; redo it if it was prefetched away)
             if (fi == 1 && w.pre_order != nullptr && w.npre >= 2 && ord.n >= 2) permutation_par(c, g, nt, nullptr, w.order, w, false);
+            done = true;
             break;
         }
         int my_accepts = 0;                              // accepted by this thread during the pass
@@ -1640,6 +1692,23 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         if (fi + 1 < ord.n) accepted_last = (int)c_reduce_d<false>(c, (double)my_accepts);     // exact: counts < 2^53
         cyc_chain += clock64() - t_mark;
     }
+    if (!last) {
+        // hand the running state to the next launch
+        c.sync();
+        if (tid < QA_NFMT && sh.cnt[tid] != 0)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&counts[tid]), (unsigned long long)(long long)sh.cnt[tid]);
+        if (c.gtid == 0) {
+            g.store(rng);
+            double* r = w.res;
+            r[0] = S[0]; r[1] = S[1]; r[2] = S[2]; r[3] = S[3];
+            r[4] = (double)degraded; r[5] = (double)chain_rounds;
+            r[6] = base_failed ? 1.0 : 0.0; r[7] = all_tiles_candidates ? 1.0 : 0.0; r[8] = (double)accepted_last;
+            r[9] = (double)cyc_perm; r[10] = (double)cyc_chain; r[11] = done ? 1.0 : 0.0;
+            r[12] = (double)n_chunks; r[13] = (double)n_cutshort;
+            stamp(first ? 5 : 7, true);
+        }
+        return;
+    }
     // max |x - y| of the final assignment (for the reported atol)
     c.sync();
     double amax = 0.0;
@@ -1664,6 +1733,7 @@ __global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict
         printf("chain nt=%d load %lld walk1+scan %lld decide %lld min3 %lld commit %lld gather %lld | chunks %u rounds %u total %lld\n", nt, cy_load, cy_scan, cy_dec, cy_min, cy_commit, cy_gather, n_chunks, chain_rounds, (long long)(clock64() - t_start));
 #endif
         state[21] = (double)c.cy_resolve; state[22] = (double)c.cy_apply; state[23] = (double)c.n_sweeps + 65536.0 * c.n_rounds;
+        stamp(first ? 5 : 7, true);
     }
 }
 
@@ -1708,6 +1778,7 @@ static ParWork carve(void* work, int64_t n) {
     w.parent = reinterpret_cast<int32_t*>(take(4 * (n + 1)));
     w.fixed = reinterpret_cast<uint8_t*>(take(n));
     w.hdr = reinterpret_cast<double*>(take(8 * HDR_DOUBLES));
+    w.res = reinterpret_cast<double*>(take(8 * HDR_DOUBLES));
     w.delta = reinterpret_cast<double*>(take(96 * n));
     w.pre_order = nullptr;
     w.pre_rng = nullptr;
@@ -1780,11 +1851,21 @@ static int launch_cluster_nostage(void (*kern)(KArgs...), int nr, cudaStream_t s
 
 using namespace qa;
 
+extern "C" int qa_debug_times(unsigned long long* out8_host, int reset) {
+    if (out8_host && cudaMemcpyFromSymbol(out8_host, qa_times, sizeof(unsigned long long) * 40) != cudaSuccess) return check_launch("qa_debug_times");
+    if (reset) {
+        unsigned long long init[40];
+        for (int i = 0; i < 40; ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+        if (cudaMemcpyToSymbol(qa_times, init, sizeof(init)) != cudaSuccess) return check_launch("qa_debug_times");
+    }
+    return 0;
+}
+
 extern "C" int qa_collective_bench(double* out, int iters, int cluster, qa_stream_t stream) {
     return launch_cluster(collective_bench_kernel, cluster, (cudaStream_t)stream, out, iters);
 }
 
-extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(n) + al(8 * HDR_DOUBLES) + al(96 * n) + 512; }
+extern "C" int64_t qa_greedy_par_work_bytes(int64_t n) { return al(4 * (n + 1)) * 8 + al(n) + 2 * al(8 * HDR_DOUBLES) + al(96 * n) + 512; }
 
 extern "C" int64_t qa_greedy_init_bytes(int64_t n) { return al(8 * HDR_DOUBLES) + al(96 * n) + 256; }
 
@@ -1829,7 +1910,10 @@ static int fill_order(const int32_t* fmt_order, int nfmt, ParOrder& ord, const c
 }
 
 static int greedy_init_launch(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
-                              bool sums, bool deltas, bool deltas_in_cluster, qa_stream_t stream, const char* who) {
+                              bool sums, bool deltas, bool deltas_in_cluster, qa_stream_t stream, const char* who,
+                              int64_t t_begin = 0, int64_t t_end = -1) {
+    if (t_end < 0) t_end = ntiles;
+    if (t_begin < 0 || t_begin >= t_end || t_end > ntiles) { set_error("%s: bad tile range", who); return 1; }
     if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !init) { set_error("%s: bad args", who); return 1; }
     if (metric != QA_METRIC_PCC && metric != QA_METRIC_MAE) { set_error("%s: metric must be pcc or mae", who); return 1; }
     ParOrder ord;
@@ -1844,8 +1928,8 @@ static int greedy_init_launch(const double* table, int64_t ntiles, int metric, c
     if (!sums) return 0;
     double* dcl = deltas_in_cluster ? delta : nullptr;
     if (metric == QA_METRIC_PCC)
-        return launch_cluster(greedy_init_kernel<true>, pick_cluster(ntiles), s, table, (int)ntiles, ord, hdr, dcl);
-    return launch_cluster(greedy_init_kernel<false>, pick_cluster(ntiles), s, table, (int)ntiles, ord, hdr, dcl);
+        return launch_cluster(greedy_init_kernel<true>, pick_cluster(ntiles), s, table, (int)ntiles, ord, hdr, dcl, (int)t_begin, (int)t_end);
+    return launch_cluster(greedy_init_kernel<false>, pick_cluster(ntiles), s, table, (int)ntiles, ord, hdr, dcl, (int)t_begin, (int)t_end);
 }
 
 extern "C" int qa_greedy_init(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
@@ -1858,15 +1942,23 @@ extern "C" int qa_greedy_init_sums(const double* table, int64_t ntiles, int metr
     return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, true, false, false, stream, "qa_greedy_init_sums");
 }
 
+extern "C" int qa_greedy_init_sums_range(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt,
+                                         void* init, int64_t tile_begin, int64_t tile_end, qa_stream_t stream) {
+    return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, true, false, false, stream, "qa_greedy_init_sums_range",
+                              tile_begin, tile_end);
+}
+
 extern "C" int qa_greedy_init_deltas(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
                                      qa_stream_t stream) {
     return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, false, true, false, stream, "qa_greedy_init_deltas");
 }
 
-extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
-                                        const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
-                                        int64_t* counts, double* state, void* work, const int32_t* pre_order,
-                                        const qa_pcg64* pre_rng, const void* init, qa_stream_t stream) {
+extern "C" int qa_greedy_assign_passes(const double* table, int64_t ntiles, double numel, int metric, double threshold,
+                                       const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
+                                       int64_t* counts, double* state, void* work, const int32_t* pre_order,
+                                       const qa_pcg64* pre_rng, const void* init, int pass_begin, int pass_end,
+                                       qa_stream_t stream) {
+    if (pass_begin < 0 || pass_end <= pass_begin || pass_begin >= nfmt) { set_error("qa_greedy_assign_passes: bad pass range"); return 1; }
     if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !rng || !assignment || !counts || !state || !work) {
         set_error("qa_greedy_assign_par: bad args");
         return 1;
@@ -1884,9 +1976,17 @@ extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, dou
     }
     if (metric == QA_METRIC_PCC)
         return launch_cluster(greedy_par_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                              metric, threshold, ord, rng, assignment, counts, state, pw, have_init);
+                              metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end);
     return launch_cluster(greedy_par_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                          metric, threshold, ord, rng, assignment, counts, state, pw, have_init);
+                          metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end);
+}
+
+extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
+                                        const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
+                                        int64_t* counts, double* state, void* work, const int32_t* pre_order,
+                                        const qa_pcg64* pre_rng, const void* init, qa_stream_t stream) {
+    return qa_greedy_assign_passes(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state, work,
+                                   pre_order, pre_rng, init, 0, nfmt, stream);
 }
 
 extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric, double threshold,

@@ -218,11 +218,11 @@ constexpr int FAST_UNROLL = 4;
 template <bool VEC, bool EXACT_ABS>
 __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_kernel(
     const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
-    int64_t chunks, int64_t nitems, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
+    int64_t chunks, int64_t item0, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
     __shared__ double part[FAST_WARPS - 1][14][32];
     __shared__ float partmx[FAST_WARPS - 1][3][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t item = blockIdx.x;
+    const int64_t item = blockIdx.x + item0;          // item0 > 0: a launch that covers a range of tile rows
     const int64_t tr = item / chunks;
     const int64_t ck = item - tr * chunks;
     const int64_t col0 = ck * 512 + (int64_t)lane * GROUP;
@@ -482,6 +482,32 @@ __global__ void __launch_bounds__(STRICT_WARPS * 32) stats_strict_kernel(
 
 using namespace qa;
 
+static int tile_stats_fast(const void* x, int64_t rows, int64_t cols, int64_t ld, uint32_t fmt_mask, int mode, double* table,
+                           int64_t tile_row_begin, int64_t tile_row_end, cudaStream_t s) {
+    const int64_t tiles_h = cdiv(rows, TILE), tiles_w = cdiv(cols, TILE), ntiles = tiles_h * tiles_w;
+    const int64_t chunks = cdiv(cols, 512);
+    const int64_t grid = (tile_row_end - tile_row_begin) * chunks, item0 = tile_row_begin * chunks;
+    const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
+    const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
+    const bool exact_abs = (mode == QA_STATS_FAST);
+    if (vec && exact_abs) stats_fast_kernel<true, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
+    else if (vec) stats_fast_kernel<true, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
+    else if (exact_abs) stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
+    else stats_fast_kernel<false, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
+    return check_launch("qa_tile_stats(fast)");
+}
+
+extern "C" int qa_tile_stats_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld, uint32_t fmt_mask, int mode,
+                                  double* table, int64_t tile_row_begin, int64_t tile_row_end, qa_stream_t stream) {
+    if (rows <= 0 || cols <= 0 || ld < cols || !table) { set_error("qa_tile_stats_rows: bad args"); return 1; }
+    if (x_dtype != QA_DT_BF16 || (mode != QA_STATS_FAST && mode != QA_STATS_FAST_APPROX_ABS)) {
+        set_error("qa_tile_stats_rows: bf16 input and a fast mode only");
+        return 1;
+    }
+    if (tile_row_begin < 0 || tile_row_end <= tile_row_begin || tile_row_end > cdiv(rows, TILE)) { set_error("qa_tile_stats_rows: bad tile-row range"); return 1; }
+    return tile_stats_fast(x, rows, cols, ld, fmt_mask & 0xFu, mode, table, tile_row_begin, tile_row_end, (cudaStream_t)stream);
+}
+
 extern "C" int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
                              int64_t vec_tail, uint32_t fmt_mask, int mode, double* table,
                              qa_stream_t stream) {
@@ -492,16 +518,7 @@ extern "C" int qa_tile_stats(const void* x, int x_dtype, int64_t rows, int64_t c
     cudaStream_t s = (cudaStream_t)stream;
     if (mode == QA_STATS_FAST || mode == QA_STATS_FAST_APPROX_ABS) {
         if (x_dtype != QA_DT_BF16) { set_error("qa_tile_stats: fast mode needs bf16 input (use QA_STATS_STRICT for fp32)"); return 1; }
-        const int64_t chunks = cdiv(cols, 512), nitems = tiles_h * chunks;
-        const int64_t grid = nitems;
-        const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
-        const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
-        const bool exact_abs = (mode == QA_STATS_FAST);
-        if (vec && exact_abs) stats_fast_kernel<true, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
-        else if (vec) stats_fast_kernel<true, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
-        else if (exact_abs) stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
-        else stats_fast_kernel<false, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, nitems, ntiles, fmt_mask, table);
-        return check_launch("qa_tile_stats(fast)");
+        return tile_stats_fast(x, rows, cols, ld, fmt_mask, mode, table, 0, tiles_h, s);
     }
     if (mode != QA_STATS_STRICT) { set_error("qa_tile_stats: bad mode"); return 1; }
     const int64_t grid = cdiv(ntiles, STRICT_WARPS);

@@ -231,7 +231,7 @@ def greedy_init(table: torch.Tensor, metric: str, fmt_order) -> torch.Tensor:
 
 
 def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor,
-                  parallel: bool | None = None, prefetched=None, init: torch.Tensor | None = None):
+                  parallel: bool | None = None, prefetched=None, init: torch.Tensor | None = None, split_at: int | None = None):
     """-> (assignment int8[ntiles], counts int64[4], state float64[24]) on device.
     parallel=None: the cluster-parallel kernel for pcc / mae, the one-thread chain for atol.
     prefetched = greedy_prefetch(...) and init = greedy_init(...) are optional stages computed ahead of time."""
@@ -249,9 +249,11 @@ def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float
         pre_order, pre_rng = prefetched if prefetched is not None else (None, None)
         if pre_order is not None and len(fmt_order) >= 3 and pre_order.shape[0] < 2:
             raise ValueError("prefetched permutations were drawn for fewer formats than fmt_order has")
-        check(L.qa_greedy_assign_par_pre(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order,
-                                         len(fmt_order), _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work),
-                                         _ptr(pre_order), _ptr(pre_rng), _ptr(init), _stream()), "qa_greedy_assign_par")
+        ranges = [(0, len(fmt_order))] if not split_at else [(0, split_at), (split_at, len(fmt_order))]
+        for b, e in ranges:          # split_at: the same run as two launches (qa_greedy_assign_passes)
+            check(L.qa_greedy_assign_passes(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order,
+                                            len(fmt_order), _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work),
+                                            _ptr(pre_order), _ptr(pre_rng), _ptr(init), b, e, _stream()), "qa_greedy_assign_par")
     else:
         work = torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
         check(L.qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),

@@ -349,6 +349,38 @@ def test_staged_permutation_matches_numpy(qa):
         eng.numpy_permutation(r2, n, parallel=False)
 
 
+def test_table_and_init_in_pieces(qa):
+    """qa_tile_stats_rows + qa_greedy_init_sums_range over consecutive pieces == the one-shot calls (table and init header)."""
+    import torch
+    from quantization_analysis_b200 import _lib
+    from quantization_analysis_b200._lib import METRIC_CODE, check
+    eng = qa["engine"]
+    L = _lib.lib()
+    x = G.algo_input("het_256x512")
+    p = eng.prepare_tiles(x)
+    fmts = list(G.MIXED)
+    order = _lib.int32_array([eng.FMT_INDEX[f] for f in fmts])
+    for exact_abs, mode in ((True, _lib.STATS_FAST), (False, _lib.STATS_FAST_APPROX_ABS)):
+        whole = eng.tile_stats(p, fmts, exact_abs=exact_abs)
+        nt = whole.shape[1]
+        pieces = torch.zeros_like(whole)
+        th = p.tiles_h
+        cuts = [0, 1, 3, th]
+        for metric in ("pcc", "mae"):
+            init_whole = eng.greedy_init(whole, metric, fmts)
+            init_pieces = torch.zeros_like(init_whole)
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                check(L.qa_tile_stats_rows(p.data.data_ptr(), _lib.QA_DT_BF16, p.rows, p.cols, p.cols, 0xF, mode, pieces.data_ptr(), a, b,
+                                           torch.cuda.current_stream().cuda_stream), "qa_tile_stats_rows")
+                check(L.qa_greedy_init_sums_range(pieces.data_ptr(), nt, METRIC_CODE[metric], order, len(fmts), init_pieces.data_ptr(),
+                                                  a * p.tiles_w, b * p.tiles_w, torch.cuda.current_stream().cuda_stream),
+                      "qa_greedy_init_sums_range")
+            assert torch.equal(whole, pieces)
+            hw = init_whole.view(torch.float64)[:7].cpu().numpy()
+            hp = init_pieces.view(torch.float64)[:7].cpu().numpy()
+            assert np.array_equal(hw, hp), (metric, hw, hp)
+
+
 def test_greedy_staged_equals_inline(qa):
     """qa_greedy_prefetch / qa_greedy_init + qa_greedy_assign_par_pre give the same map, counts, state and stream
     position as the kernel that does everything inline, in every combination of stages - including a base state that
@@ -379,6 +411,13 @@ def test_greedy_staged_equals_inline(qa):
                 assert torch.equal(a1, a2) and torch.equal(c1, c2), (metric, thr, fmts, use_pre, use_init)
                 assert torch.equal(r1, r2), (metric, thr, fmts, use_pre, use_init)
                 assert torch.equal(s1[:8], s2[:8])
+                if len(fmts) >= 3:          # the same run as two launches (passes [0,2) and [2,n)) and as three
+                    for cut in (1, 2):
+                        r3 = eng.make_rng(31)
+                        a3, c3, s3 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r3, parallel=True, prefetched=pre, init=init,
+                                                       split_at=cut)
+                        assert torch.equal(a1, a3) and torch.equal(c1, c3) and torch.equal(r1, r3), (metric, thr, fmts, cut)
+                        assert torch.equal(s1[:8], s3[:8])
     assert seen_spec and seen_nospec
 
 
