@@ -35,7 +35,7 @@ namespace cg = cooperative_groups;
 
 namespace qa {
 
-constexpr int GT = 512;           // threads per CTA
+constexpr int GT = 256;           // threads per CTA
 constexpr int NW = GT / 32;
 constexpr int MAXR = 16;          // largest cluster
 constexpr int DPT = 8;            // draws per thread per round (4 LCG outputs)
@@ -1056,7 +1056,6 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
     Sh& sh = c.sh;
     const int tid = threadIdx.x;
     constexpr int HEAD = 192;
-    static_assert(HEAD <= GT, "head is staged by one CTA pass");
     int events[NC];
 #pragma unroll
     for (int s = 0; s < NC; ++s) events[s] = 0;
@@ -1071,7 +1070,7 @@ __device__ void faithful_init_sums(Coop& c, const double* const (&col)[NC], int 
         __syncthreads();
 #pragma unroll
         for (int s = 0; s < NC; ++s)
-            if (tid < pos) qa_stage[s * HEAD + tid] = col[s][tid];
+            for (int i = tid; i < pos; i += GT) qa_stage[s * HEAD + i] = col[s][i];
         __syncthreads();
         if (tid < NC) {
             double acc = 0.0;

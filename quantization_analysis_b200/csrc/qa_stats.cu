@@ -206,7 +206,10 @@ __device__ __forceinline__ void load_row_group(const uint16_t* __restrict__ x, i
 
 constexpr int FAST_WARPS = 4;               // warps per CTA; one CTA = one 32-row x 512-column item
 constexpr int FAST_RPW = TILE / FAST_WARPS; // rows per warp
-constexpr int FAST_UNROLL = 4;
+#ifndef FAST_UNROLL_N
+#define FAST_UNROLL_N 4
+#endif
+constexpr int FAST_UNROLL = FAST_UNROLL_N;
 #ifndef FAST_MIN_BLOCKS
 #define FAST_MIN_BLOCKS 4
 #endif
