@@ -254,8 +254,10 @@ class GreedyBatch:
             out.append(row)
         return out
 
-    def run_from_host(self, host_tensors) -> list[dict]:
-        """End-to-end pass: pinned host bf16 -> device, quantize+score+assign, results back to host."""
+    def enqueue_from_host(self, host_tensors) -> None:
+        """End-to-end pass, asynchronous half: pinned host bf16 -> device, quantize+score+assign, results into pinned host
+        buffers.  Returns immediately; ``finish()`` waits for this pass only, so a caller with two batches can keep the
+        PCIe link busy with the next list's inputs while this one computes."""
         cur = torch.cuda.current_stream(self.device)
         order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])
         for k, i in enumerate(order):
@@ -264,26 +266,51 @@ class GreedyBatch:
             with torch.cuda.stream(st):
                 self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
                 self._enqueue(self.slots[i], st, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
+                self._d2h(self.slots[i])                     # behind this tensor's chain, on its own stream
+        self._pending = torch.cuda.Event()
+        if not hasattr(self, "_join_stream"):
+            self._join_stream = torch.cuda.Stream(device=self.device)
+        join = self._join_stream
         for st in self.streams:
-            cur.wait_stream(st)
-        return self.collect()
+            join.wait_stream(st)
+        self._pending.record(join)
+
+    def _d2h(self, s) -> None:
+        if "h_assignment" not in s:
+            s["h_assignment"] = torch.empty(s["ntiles"], dtype=torch.int8).pin_memory()
+            s["h_counts"] = torch.empty(NFMT, dtype=torch.int64).pin_memory()
+            s["h_state"] = torch.empty(24, dtype=torch.float64).pin_memory()
+        s["h_assignment"].copy_(s["assignment"], non_blocking=True)
+        s["h_counts"].copy_(s["counts"], non_blocking=True)
+        src = s["sums"] if self.metric == "atol" else s["state"]
+        s["h_state"][: src.numel()].copy_(src, non_blocking=True)
+
+    def finish(self) -> list[dict]:
+        """Wait for the pass started by ``enqueue_from_host`` and return its results."""
+        self._pending.synchronize()
+        return [self._result(s, s["h_assignment"], s["h_counts"], s["h_state"][: (8 if self.metric == "atol" else 24)]) for s in self.slots]
+
+    def run_from_host(self, host_tensors) -> list[dict]:
+        """End-to-end pass: pinned host bf16 -> device, quantize+score+assign, results back to host."""
+        self.enqueue_from_host(host_tensors)
+        return self.finish()
+
+    def _result(self, s, a, c, sums) -> dict:
+        counts = {f: int(c[i]) for i, f in enumerate(MIXED)}
+        v = sums.numpy()
+        if self.metric != "atol":      # state = {sx, sx2, sy, sy2, sxy, sabs, flags, value, cycles x3, max|x-y|, ...}
+            v = np.array([v[0], v[1], v[2], v[3], v[4], v[5], v[11]])
+        return {"assignment": a.numpy().reshape(-(-s["rows"] // 32), -(-s["cols"] // 32)).copy(), "counts": counts,
+                "metrics": engine.metrics_from_sums(v, s["numel"]), "state": sums.numpy().copy()}
 
     def collect(self) -> list[dict]:
         """Device -> host: assignment maps, counts and exact pcc/mae/atol per tensor (synchronises)."""
-        out = []
         packs = []
         for s in self.slots:
             packs.append((s["assignment"].to("cpu", non_blocking=True), s["counts"].to("cpu", non_blocking=True),
                           (s["sums"] if self.metric == "atol" else s["state"]).to("cpu", non_blocking=True)))
         torch.cuda.current_stream(self.device).synchronize()
-        for s, (a, c, sums) in zip(self.slots, packs):
-            counts = {f: int(c[i]) for i, f in enumerate(MIXED)}
-            v = sums.numpy()
-            if self.metric != "atol":      # state = {sx, sx2, sy, sy2, sxy, sabs, flags, value, cycles x3, max|x-y|, ...}
-                v = np.array([v[0], v[1], v[2], v[3], v[4], v[5], v[11]])
-            out.append({"assignment": a.numpy().reshape(-(-s["rows"] // 32), -(-s["cols"] // 32)), "counts": counts,
-                        "metrics": engine.metrics_from_sums(v, s["numel"]), "state": sums.numpy().copy()})
-        return out
+        return [self._result(s, a, c, sums) for s, (a, c, sums) in zip(self.slots, packs)]
 
     def d2h_bytes(self) -> int:
         return sum(s["ntiles"] + 8 * NFMT + 8 * 8 for s in self.slots)

@@ -520,3 +520,24 @@ def test_batch_graph_replay_equals_eager(qa):
             assert np.array_equal(e["assignment"], g["assignment"])
             assert e["counts"] == g["counts"]
             assert np.array_equal(e["state"][:8], g["state"][:8])
+
+
+def test_batch_from_host_async_equals_sync(qa):
+    """enqueue_from_host / finish on two alternating batches == run_from_host == device-resident run."""
+    from quantization_analysis_b200.batch import GreedyBatch
+    from quantization_analysis_b200 import synthetic
+    shapes = [(256, 512), (96, 320)]
+    xs = [synthetic.randn_bf16_cpu(s, 60 + i).pin_memory() for i, s in enumerate(shapes)]
+    b0 = GreedyBatch(shapes, metric="pcc", threshold=0.999, seed=9)
+    b1 = GreedyBatch(shapes, metric="pcc", threshold=0.999, seed=9)
+    want = b0.run_from_host(xs)
+    b0.enqueue_from_host(xs)
+    b1.enqueue_from_host(xs)
+    for got in (b0.finish(), b1.finish()):
+        for w, g in zip(want, got):
+            assert np.array_equal(w["assignment"], g["assignment"]) and w["counts"] == g["counts"]
+            assert np.array_equal(w["state"][:8], g["state"][:8])
+    b0.load_device(xs)
+    b0.run()
+    for w, g in zip(want, b0.collect()):
+        assert np.array_equal(w["assignment"], g["assignment"]) and w["counts"] == g["counts"]
