@@ -38,28 +38,32 @@ md = ["# Round 1 - measured numbers of record (B200, sm_100a)", "",
       "Regenerate with `python profiles/make_summary.py <tag>`; raw artefacts are committed beside this file.", "",
       "## bench.py (cfg2: mixed-tile-greedy pcc>=0.999 over the five layer-0 self_attn shapes, 374 MB of bf16 per step)", "",
       f"`python bench.py --steps {b['steps']} --warmup {b['warmup']}` on one B200 (SM clock {b['clocks']['sm_mhz']} MHz, throttle reasons {b['clocks']['reasons']}):", "",
-      f"* device-resident throughput (`value`): **{b['value']:.1f} GB/s** ({b['ms_per_step']:.3f} ms per step, {b['pct_of_8TBs']:.2f} % of 8 TB/s)",
+      f"* device-resident throughput (`value`): **{b['value']:.1f} GB/s** ({b['ms_per_step']:.3f} ms per step with two double-buffered tensor lists in flight, {b['pct_of_8TBs']:.2f} % of 8 TB/s; one step alone: {b.get('step_latency_ms', float('nan')):.3f} ms)",
       f"* end to end from pinned host bf16 (`e2e`): **{b['e2e']['value']:.1f} GB/s** (H2D {b['e2e']['h2d_bytes_per_step']/1e6:.0f} MB per step: PCIe-bound)",
       f"* CPU port of the reference algorithm on the box's host cores: **{b['cpu_baseline']['value']*1e3:.2f} MB/s** ({b['cpu_baseline']['cores']} processes, {b['cpu_baseline']['host_cpus']} host CPUs)",
       "", "| kernel | ms/step (CUDA events) | algorithmic GB/s | fraction of the measured 6547 GB/s copy peak |", "|---|---:|---:|---:|"]
 for k in b["roofline_by_kernel"]:
     md.append(f"| `{k['kernel']}` | {k['ms_per_step']:.3f} | {k['achieved_gbs']:.1f} | {k['frac']:.4f} |")
-md += ["", "Round-1 history of the same bench: one-thread greedy 0.87 GB/s (415 ms/step) -> block-parallel 27 GB/s -> thread-block",
-       "cluster with DSMEM exchange 141 GB/s -> no binade cuts from sum|x-y| / sum y 262 GB/s -> cheaper collectives 276 GB/s",
-       "-> permutation prefetch on a side stream ~300 GB/s.",
-       "Stats kernel: 16 % -> 27 % (packed f32x2, xorsign clamp) -> 28 % (one CTA per 32x512 item).", "",
+md += ["", "Round-1 history of the same bench: one-thread greedy 0.87 GB/s (415 ms/step) -> block-parallel 27 -> thread-block cluster with",
+       "DSMEM exchange 141 -> cheaper collectives + prefetch of two permutations 298 -> prefetch / init / chain kernels, 32-byte delta",
+       "records, speculative third permutation 412 -> one CUDA graph per step 477 -> order-free pass shortcut, EPS 8 531 -> chained",
+       "resolve, serialized tile-stat passes, priority streams 658 -> pipelined table / init sums, split chain, two lists in flight 837",
+       "-> 256-thread cluster CTAs (tile-stat CTAs co-reside) ~920.",
+       "Stats kernel: 16 % -> 27 % (packed f32x2, xorsign clamp) -> 28-29 % (one CTA per 32x512 item).", "",
        "## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`, same command; serialised and cold: compare shares)", ""] + L + ["",
        "## ncu --set full, first captured launch per kernel (o_proj 7168x16384 = 117.4 M elements)", ""]
 for d in K:
     md.append(f"### `{d['kernel']}`")
     md += [f"* {w} = {d[w]}" for w in want if w in d]
     md.append("")
-md += ["Reading.  `stats_fast_kernel`: DRAM traffic (235 MB read + 16 MB written before the kernel ends) equals the algorithmic bytes",
-       "(234.9 MB + 20.2 MB table): x is read exactly once.  26 instructions per element, issue slots ~65 % busy, FMA/ALU/XU(F2F)",
-       "pipes at 31/38/34 %: the kernel is instruction-bound (the FMA-pipe floor alone is ~70 us for this launch vs 36 us of HBM time).",
-       "`greedy_par_kernel`: one 16-CTA cluster, latency-bound (about 250 cluster-wide collectives of ~2k cycles and the L2 gathers of the",
-       "permutation); its DRAM traffic is the 20 MB table.  It is the critical path of the 5-tensor cfg2 step; with many tensors per GPU",
-       "(cfg5) the clusters of different tensors run side by side.",
+md += ["Reading.  `stats_fast_kernel`: DRAM traffic equals the algorithmic bytes (x is read exactly once; the table is written once).",
+       "26 instructions per element, issue slots ~65 % busy, FMA/ALU/XU(F2F) pipes at 31/38/34 %: the kernel is instruction-bound (the",
+       "FMA-pipe floor alone is ~70 us for o_proj vs 36 us of HBM time); the build-flag sweep `profiles/stats_variants.sh` (occupancy 4/5/6",
+       "CTAs per SM x 2/4/8 rows of loads in flight) confirms the shipped point.  The greedy kernels (`perm_resolve*`, `greedy_init_kernel`,",
+       "`greedy_par_kernel`) are one cluster per tensor and latency-bound: their DRAM traffic is the 20 MB table plus 11 MB of delta records.",
+       "A step's critical path is stats -> init sums -> chain of the largest tensor; `profiles/step_variants.py` prints the device-timestamp",
+       "timeline (o_proj alone: resolve 0-152 us | tile-stat 0-137 us | init sums over three table ranges 27-236 us -> chain passes 0-1",
+       "241-339 us -> passes 2-3 344-499 us).",
        "", "## Other kernels of the path (CUDA events, 10 launches each, o_proj-size tensor 7168x16384 unless noted)", "",
        "| kernel | what | time | algorithmic GB/s | fraction of copy peak |", "|---|---|---:|---:|---:|",
        "| `recon_fast_kernel` | cfg1 `none`: bfp8+bfp4+bfp2 reconstructions in one pass (8 B/elem) | 0.153 ms | 6123 | 0.94 |",
@@ -67,7 +71,7 @@ md += ["Reading.  `stats_fast_kernel`: DRAM traffic (235 MB read + 16 MB written
        "| `apply_fast_kernel` | final MIXED reconstruction from a tile map (4 B/elem) | 0.085 ms | 5505 | 0.84 |",
        "| `stats_fast_kernel` | quantize + tile statistics (2.17 B/elem) | 0.144 ms | 1772 | 0.27 |",
        "| `tile_scores_kernel` | NumPy-float32-faithful tile scores, 4 formats x 3 metrics (threshold / sweep) | 0.72 ms | 327 (input) | 0.05 |",
-       "| `greedy_par_kernel` | o_proj, 114 688 tiles, 4 passes | 1.2 ms | - | latency-bound |"]
+       "| greedy kernels | o_proj, 114 688 tiles, 4 passes: resolve x3 224 us + 2 x apply 34 us (side streams), init sums 119 us, chain 235 us | - | - | latency-bound |"]
 open("profiles/r1_summary.md", "w").write("\n".join(md) + "\n")
 for f in (f"bench_{tag}.json", f"launches_{tag}.csv", f"{tag}_raw.csv"):
     shutil.copy(g + f, "profiles/" + f)
