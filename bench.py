@@ -321,11 +321,11 @@ def main() -> None:
          "ms_per_step": ms_assign, "launches_per_step": batch.launches_per_step - n_stats_launches, "alg_bytes_per_step": alg_assign,
          "achieved_gbs": alg_assign / (ms_assign * 1e-3) / 1e9},
     ]
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (the o_proj tensor, 117.4 M elements), from the
-    # `ncu --set full` capture summarised in profiles/r1_summary.md (algorithmic bytes of that launch: stats
-    # 234.9 MB + 20.2 MB table = 255.1 MB; greedy 20.2 MB table + 0.1 MB map)
-    ncu_traffic = {"stats_fast_kernel": 234932224 + 16146944, "greedy_par_kernel": 18241792 + 74752}
-    ncu_traffic[kernels[1]["kernel"]] = ncu_traffic["greedy_par_kernel"]
+    # dram__bytes_read.sum + dram__bytes_write.sum of the o_proj tensor (117.4 M elements), from the `ncu --set full` captures
+    # summarised in profiles/r1_summary.md.  stats: its three row-range launches, 235.0 MB read + 10.6 MB written before the
+    # kernels end (algorithmic: 234.9 MB + 20.2 MB table).  greedy: the two chain launches 12.4 MB + init sums 0.6 MB
+    # (algorithmic: 20.2 MB table once; the delta records and the table mostly hit in L2).
+    ncu_traffic = {"stats_fast_kernel": 235032320 + 10577920, kernels[1]["kernel"]: 4258048 + 8105216 + 591360}
     dom = max(kernels, key=lambda k: k["ms_per_step"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": dom["achieved_gbs"] / peak, "traffic": ncu_traffic.get(dom["kernel"]),

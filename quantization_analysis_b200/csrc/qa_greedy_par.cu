@@ -1328,8 +1328,11 @@ __global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restr
 // ---------------------------------------------------------------------------------------------
 // the greedy kernel
 // ---------------------------------------------------------------------------------------------
+#ifndef QA_CHAIN_MIN_BLOCKS
+#define QA_CHAIN_MIN_BLOCKS 1
+#endif
 template <bool PCC>
-__global__ void __launch_bounds__(GT) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
+__global__ void __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
                                                         int64_t* counts, double* state, ParWork w, int have_init, int fi_begin,
                                                         int fi_end) {
