@@ -182,6 +182,11 @@ int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, 
                              const int32_t* pre_order, const qa_pcg64* pre_rng, const void* init,
                              qa_stream_t stream);
 
+/* Upper bound on the thread-block cluster size of the greedy kernels (1, 2, 4, 8, 16; 0 = automatic: large tensors get
+ * 16 CTAs for latency).  A caller with many tensors in flight trades per-tensor latency for SM time with a smaller
+ * cluster; results do not depend on the cluster size.  Process-wide; returns the previous value. */
+int qa_greedy_cluster_cap(int max_cluster);
+
 /* Diagnostic timeline: device timestamps (ns) {first start, last end} of the cluster kernels since the last reset -
  * resolve chain, init sums, chain launch containing pass 0, later chain launch - one row of 8 per cluster-size class
  * (log2 of the cluster size, 0..4).  out8_host: HOST array of 40 (may be NULL); reset != 0 re-arms the slots.  Synchronous (cudaMemcpy{From,To}Symbol). */

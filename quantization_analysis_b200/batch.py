@@ -26,7 +26,10 @@ class GreedyBatch:
         self.metric, self.threshold, self.seed = metric, float(threshold), int(seed)
         self.tile_formats = list(tile_formats)
         self.shapes = [tuple(int(v) for v in s) for s in shapes]
-        n_streams = min(16, len(self.shapes)) if n_streams is None else n_streams     # one stream per tensor
+        # one stream per tensor; a long list (one MoE layer = hundreds of equal tensors) is throughput-bound on SM time, not
+        # on one tensor's latency: more tensors in flight on smaller clusters (cluster_cap, applied while enqueueing)
+        self.cluster_cap = 2 if len(self.shapes) > 32 else 0
+        n_streams = min(32 if self.cluster_cap else 16, len(self.shapes)) if n_streams is None else n_streams
         # Cluster kernels (resolve / init / chain) can only start when a whole GPC's worth of SMs is free at once, which a
         # streaming kernel that keeps refilling every SM rarely allows: they go on high-priority streams, the tile-stat
         # kernels on normal-priority ones, so the block scheduler drains SMs for a pending cluster first.
@@ -43,9 +46,17 @@ class GreedyBatch:
         L = _lib.lib()
         self.slots = []
         rng0 = engine.make_rng(self.seed, self.device)
-        for (r, c) in self.shapes:
-            nt = (-(-r // 32)) * (-(-c // 32))
+        # Permutations #1..#3 depend only on (seed, ntiles): tensors with the same tile count share them (every expert of a
+        # MoE layer, every layer of a model).  The first such tensor in run order (largest first) draws them.
+        nts = [(-(-r // 32)) * (-(-c // 32)) for (r, c) in self.shapes]
+        leader_of = {}
+        for i in sorted(range(len(nts)), key=lambda i: -nts[i]):
+            leader_of.setdefault(nts[i], i)
+        for idx, (r, c) in enumerate(self.shapes):
+            nt = nts[idx]
+            lead = leader_of[nt] == idx
             self.slots.append({
+                "leader": leader_of[nt],
                 "rows": r, "cols": c, "ntiles": nt, "numel": r * c,
                 "x": torch.empty(r * c, dtype=torch.bfloat16, device=self.device),
                 "table": torch.zeros((NSTAT, nt), dtype=torch.float64, device=self.device),
@@ -56,15 +67,20 @@ class GreedyBatch:
                 "work": torch.empty(max(L.qa_greedy_work_bytes(nt), L.qa_greedy_par_work_bytes(nt)), dtype=torch.uint8,
                                     device=self.device),
                 "rng": rng0.clone(),
-                "pre_order": torch.empty((2, nt), dtype=torch.int32, device=self.device),
-                "rngs": torch.stack([rng0, rng0, rng0]).contiguous(),      # stream states after permutations #1, #2, #3
+                "pre_order": torch.empty((2, nt), dtype=torch.int32, device=self.device) if lead else None,
+                "rngs": torch.stack([rng0, rng0, rng0]).contiguous() if lead else None,   # stream states after permutations #1, #2, #3
                 "init": torch.empty(L.qa_greedy_init_bytes(nt), dtype=torch.uint8, device=self.device),
-                "jarr": torch.empty((3, nt), dtype=torch.int32, device=self.device),
-                "apply_work": torch.empty((2, L.qa_perm_apply_work_bytes(nt)), dtype=torch.uint8, device=self.device),
+                "jarr": torch.empty((3, nt), dtype=torch.int32, device=self.device) if lead else None,
+                "apply_work": torch.empty((2, L.qa_perm_apply_work_bytes(nt)), dtype=torch.uint8, device=self.device) if lead else None,
                 "ev": torch.cuda.Event(),
+                "ev_a2": torch.cuda.Event(),
+                "ev_a3": torch.cuda.Event(),
                 "ev2": torch.cuda.Event(),
                 "ev3": torch.cuda.Event(),
             })
+        for s_ in self.slots:                 # followers read the leader's permutations
+            ld = self.slots[s_["leader"]]
+            s_["pre_order"], s_["rngs"] = ld["pre_order"], ld["rngs"]
         self._rng0 = rng0
         self._graphs = {}
         self.trace = None            # set to {} to record per-tensor stage events during eager run() (see timeline())
@@ -79,7 +95,10 @@ class GreedyBatch:
             elif not self.prefetch:
                 n = 4
             else:
-                n = (5 + 2 + 2 * 7) if len(self.tile_formats) >= 3 else (4 + 1 + 7)
+                lead = self.slots[s["leader"]] is s
+                n = 5 if len(self.tile_formats) >= 3 else 4
+                if lead:
+                    n += (2 + 2 * 7) if len(self.tile_formats) >= 3 else (1 + 7)
             if metric != "atol" and s["ntiles"] >= self.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8:
                 n += 4
             self.launches_per_step += n
@@ -106,7 +125,13 @@ class GreedyBatch:
                 self.trace.setdefault(id(slot), {})[tag] = ev
 
         mark("start")
-        if pre:
+        lead = self.slots[slot["leader"]] is slot
+        if pre and not lead:
+            side, side2 = side
+            side2.wait_stream(stream)
+            with torch.cuda.stream(side2):
+                slot["rng"].copy_(self._rng0, non_blocking=True)      # off the stats -> init -> chain path
+        if pre and lead:
             # the first permutations depend only on (seed, ntiles): draw them on side streams while the tile-stat pass
             # streams the tensor.  Resolves chain through the RNG state (#1 -> #2 -> #3, one cluster each); each apply
             # only needs its own swap targets and runs as grid kernels, #2's on a second side stream next to resolve #3.
@@ -131,14 +156,17 @@ class GreedyBatch:
                 side2.wait_event(slot["ev"])
                 check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
                                       slot["apply_work"][0].data_ptr(), side2.cuda_stream), "qa_perm_apply")
+                slot["ev_a2"].record(side2)
                 check(L.qa_perm_resolve(slot["rngs"][1].data_ptr(), n, slot["jarr"][2].data_ptr(), slot["rngs"][2].data_ptr(), sa),
                       "qa_perm_resolve")
                 check(L.qa_perm_apply(slot["jarr"][2].data_ptr(), n, None, slot["pre_order"][1].data_ptr(),
                                       slot["apply_work"][1].data_ptr(), sa), "qa_perm_apply")
+                slot["ev_a3"].record(side)
             else:
                 check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
                                       slot["apply_work"][0].data_ptr(), sa), "qa_perm_apply")
-        if pre:
+                slot["ev_a2"].record(side)
+        if pre and lead:
             mark("prefetch", side)
         mode = STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS
         iargs = (slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order, len(self.tile_formats),
@@ -173,7 +201,7 @@ class GreedyBatch:
             stream.wait_stream(ss)
             mark("stats")
         if assign:
-            if not (pre and len(self.tile_formats) >= 3):
+            if not pre or (lead and len(self.tile_formats) < 3):
                 slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
             args = (slot["table"].data_ptr(), slot["ntiles"], float(slot["numel"]),
                     METRIC_CODE[self.metric], self.threshold, self._order, len(self.tile_formats),
@@ -196,16 +224,19 @@ class GreedyBatch:
                 pargs = args + (slot["pre_order"].data_ptr() if pre else None, slot["rngs"][1].data_ptr() if pre else None,
                                 slot["init"].data_ptr())
                 nf = len(self.tile_formats)
+                ld = self.slots[slot["leader"]]
                 if pre and nf >= 3:
                     # passes 0-1 only need permutation #2 (applied on side2 while #3 is still being drawn); the later
-                    # passes wait for the speculative #3 (applied last on the side stream)
-                    stream.wait_stream(side2)
+                    # passes wait for the speculative #3 (applied last on the leader's side stream)
+                    stream.wait_stream(side2)                 # own seed copy (and, for a leader, apply #2)
+                    stream.wait_event(ld["ev_a2"])
                     check(L.qa_greedy_assign_passes(*pargs, 0, 2, sp), "qa_greedy_assign_passes")
-                    stream.wait_stream(side)
+                    stream.wait_event(ld["ev_a3"])
                     check(L.qa_greedy_assign_passes(*pargs, 2, nf, sp), "qa_greedy_assign_passes")
                 else:
                     if pre:
-                        stream.wait_stream(side)
+                        stream.wait_stream(side2 if not lead else side)
+                        stream.wait_event(ld["ev_a2"])
                     check(L.qa_greedy_assign_passes(*pargs, 0, nf, sp), "qa_greedy_assign_passes")
             mark("chain")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
@@ -216,6 +247,13 @@ class GreedyBatch:
         """Enqueue one pass over every tensor; returns immediately (no host sync)."""
         cur = torch.cuda.current_stream(self.device)
         order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])   # longest chain first
+        prev_cap = _lib.lib().qa_greedy_cluster_cap(self.cluster_cap)
+        try:
+            self._run_ordered(cur, order, stats, assign)
+        finally:
+            _lib.lib().qa_greedy_cluster_cap(prev_cap)
+
+    def _run_ordered(self, cur, order, stats, assign) -> None:
         for k, i in enumerate(order):
             st = self.streams[k % len(self.streams)]
             st.wait_stream(cur)
@@ -260,6 +298,9 @@ class GreedyBatch:
         PCIe link busy with the next list's inputs while this one computes."""
         cur = torch.cuda.current_stream(self.device)
         order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])
+        if getattr(self, "_pending", None) is not None:
+            cur.wait_event(self._pending)             # a pass still in flight on these buffers goes first
+        prev_cap = _lib.lib().qa_greedy_cluster_cap(self.cluster_cap)
         for k, i in enumerate(order):
             st = self.streams[k % len(self.streams)]
             st.wait_stream(cur)
@@ -267,6 +308,7 @@ class GreedyBatch:
                 self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
                 self._enqueue(self.slots[i], st, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
                 self._d2h(self.slots[i])                     # behind this tensor's chain, on its own stream
+        _lib.lib().qa_greedy_cluster_cap(prev_cap)
         self._pending = torch.cuda.Event()
         if not hasattr(self, "_join_stream"):
             self._join_stream = torch.cuda.Stream(device=self.device)

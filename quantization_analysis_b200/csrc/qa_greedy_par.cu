@@ -1788,7 +1788,15 @@ static ParWork carve(void* work, int64_t n) {
     return w;
 }
 
+static int pick_cluster_auto(int64_t n);
+static int g_cluster_cap = 0;       // qa_greedy_cluster_cap: upper bound on the cluster size (0 = none)
+
 static int pick_cluster(int64_t n) {
+    const int r = pick_cluster_auto(n);
+    return g_cluster_cap > 0 && r > g_cluster_cap ? g_cluster_cap : r;
+}
+
+static int pick_cluster_auto(int64_t n) {
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("QA_GREEDY_CLUSTER");
@@ -1861,6 +1869,12 @@ extern "C" int qa_debug_times(unsigned long long* out8_host, int reset) {
         if (cudaMemcpyToSymbol(qa_times, init, sizeof(init)) != cudaSuccess) return check_launch("qa_debug_times");
     }
     return 0;
+}
+
+extern "C" int qa_greedy_cluster_cap(int max_cluster) {
+    const int prev = g_cluster_cap;
+    g_cluster_cap = max_cluster < 0 ? 0 : (max_cluster > MAXR ? MAXR : max_cluster);
+    return prev;
 }
 
 extern "C" int qa_collective_bench(double* out, int iters, int cluster, qa_stream_t stream) {
