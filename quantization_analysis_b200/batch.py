@@ -17,8 +17,8 @@ MIXED = engine.MIXED_FORMATS
 
 
 class GreedyBatch:
-    PIPELINE_MIN_TILES = 65536      # tensors at least this large produce their table in two pieces (see _enqueue)
-    PIPELINE_FIRST_TILES = 16384    # ... the first of about this many tiles
+    PIPELINE_MIN_TILES = 32768      # tensors at least this large produce their table in three row ranges (see _enqueue)
+    PIPELINE_FIRST_TILES = 4096    # ... the first of at least this many tiles (or an eighth of the tensor)
 
     def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
                  tile_formats=MIXED, n_streams: int | None = None, device=None):
@@ -181,7 +181,8 @@ class GreedyBatch:
                 # Large tensor: the sequential initial sums spend most of their rounds on the first few thousand tiles
                 # (the running sums double often while they are small).  Produce the table in two pieces and let the
                 # sums over the first piece run while the tile-stat pass streams the rest of the tensor.
-                split = max(1, min(tiles_h - 2, -(-self.PIPELINE_FIRST_TILES // tiles_w)))
+                first = max(self.PIPELINE_FIRST_TILES, slot["ntiles"] // 8)       # first cut: about an eighth of the tiles
+                split = max(1, min(tiles_h - 2, -(-first // tiles_w)))
                 split2 = max(split + 1, tiles_h // 2)                      # second cut: half of the tensor
                 sargs = (slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0xF, mode,
                          slot["table"].data_ptr())
