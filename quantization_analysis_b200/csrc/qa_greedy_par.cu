@@ -276,6 +276,43 @@ __device__ __forceinline__ double c_reduce_d(Coop& c, double v) {
     return t;
 }
 
+// c_reduce_d<false> for NV values at once: the same fixed tree per value (lanes, warps in order, CTAs in order), one
+// pair of CTA barriers and one exchange for all of them
+template <int NV>
+__device__ __forceinline__ void c_reduce_sum_multi(Coop& c, double (&v)[NV]) {
+    static_assert(NV <= 12 && NW * NV <= NW * 4 * 2 * 2, "payload / staging slots");
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+            v[k] = v[k] + __hiloint2double(__shfl_xor_sync(0xFFFFFFFFu, __double2hiint(v[k]), o),
+                                           __shfl_xor_sync(0xFFFFFFFFu, __double2loint(v[k]), o));
+        if ((threadIdx.x & 31) == 0) c.sh.i64[(threadIdx.x >> 5) * NV + k] = __double_as_longlong(v[k]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double r = __longlong_as_double(c.sh.i64[k]);
+        for (int i = 1; i < NW; ++i) r = r + __longlong_as_double(c.sh.i64[i * NV + k]);
+        v[k] = r;
+    }
+    __syncthreads();
+    if (c.nr == 1) return;
+    const unsigned b = c.par & 1u;
+    if (threadIdx.x < c.nr) {
+        long long* dst = c.cl.map_shared_rank(&c.sh.xl[b][c.rank][0], threadIdx.x);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dst[k] = __double_as_longlong(v[k]);
+    }
+    c.xarrive_wait();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double t = __longlong_as_double(c.sh.xl[b][0][k]);
+        for (unsigned q = 1; q < c.nr; ++q) t = t + __longlong_as_double(c.sh.xl[b][q][k]);
+        v[k] = t;
+    }
+}
+
 // One thread of the cluster (owner) publishes n <= 8 doubles to every CTA; all threads read them back.
 __device__ __forceinline__ void c_bcast_d(Coop& c, bool owner, const double* vals, int n, double* out) {
     const unsigned b = c.par & 1u;
@@ -1202,6 +1239,9 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
     const long long t_start = clock64();
     double sx = 0.0, sx2 = 0.0;
     double S[4] = {0.0, 0.0, 0.0, 0.0};      // sy, sy2, sxy, sabs (mae uses S[3] only)
+    double dr_sum[QA_NFMT - 1];              // per transition: sum |delta sy| over all tiles (pcc)
+#pragma unroll
+    for (int tr = 0; tr + 1 < QA_NFMT; ++tr) dr_sum[tr] = 0.0;
     unsigned degraded = 0;
     if (PCC) {
         {   // sums of non-negative terms: few binade changes, always carried faithfully
@@ -1226,14 +1266,29 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
             double R[2];
             bool walk[2];
             const long long ti = clock64();
+            // one pass over the tiles for everything that is a plain fixed-order sum: sum / sum|.| of the two signed
+            // columns and, per format transition, sum |delta sy| (bounds how far sy can drift during that pass)
+            double acc[4 + QA_NFMT - 1];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                double sm = 0.0, sa = 0.0;
-                for (int i = c.gtid; i < nt; i += c.gth) { const double v = cols[q][i]; sm += v; sa += fabs(v); }
-                R[q] = c_reduce_d<false>(c, sm);
-                sa = c_reduce_d<false>(c, sa);
-                walk[q] = fabs(R[q]) < 0.25 * sa;
+            for (int q = 0; q < 4 + QA_NFMT - 1; ++q) acc[q] = 0.0;
+#pragma unroll 2
+            for (int i = c.gtid; i < nt; i += c.gth) {
+                const double vx = cols[0][i];
+                double vy[QA_NFMT];
+#pragma unroll
+                for (int f = 0; f < QA_NFMT; ++f) vy[f] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], 0) * nt + i] : 0.0;
+                acc[0] += vx; acc[1] += fabs(vx);
+                acc[2] += vy[0]; acc[3] += fabs(vy[0]);
+#pragma unroll
+                for (int tr = 0; tr + 1 < QA_NFMT; ++tr)
+                    if (tr + 1 < ord.n) acc[4 + tr] += fabs(__dsub_rn(vy[tr + 1], vy[tr]));
             }
+            c_reduce_sum_multi<4 + QA_NFMT - 1>(c, acc);
+            R[0] = acc[0]; R[1] = acc[2];
+            walk[0] = fabs(R[0]) < 0.25 * acc[1];
+            walk[1] = fabs(R[1]) < 0.25 * acc[3];
+#pragma unroll
+            for (int tr = 0; tr + 1 < QA_NFMT; ++tr) dr_sum[tr] = acc[4 + tr];
             if (walk[0] && walk[1]) degraded = 3u;
             else faithful_init_sums<2>(c, cols, 0, nt, R, degraded, 24);
             c.cy_i1 += clock64() - ti;
@@ -1252,9 +1307,6 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
     }
     // delta[tr][t] = stats(fmt[tr+1]) - stats(fmt[tr]) of tile t: one 32-byte record per tile and transition, so the
     // chain fetches a visited tile with one sector instead of eight
-    double dr[QA_NFMT - 1];                      // per transition: sum |delta sy| over all tiles (bounds the drift of sy)
-#pragma unroll
-    for (int tr = 0; tr + 1 < QA_NFMT; ++tr) dr[tr] = 0.0;
     if (build_deltas) {
         for (int t = c.gtid; t < nt; t += c.gth) {
             double v[QA_NFMT][4];
@@ -1266,30 +1318,14 @@ __device__ void init_phase(Coop& c, const double* __restrict__ table, int nt, co
             for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
                 if (tr + 1 >= ord.n) break;
                 double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
-                const double d0 = __dsub_rn(v[tr + 1][0], v[tr][0]);
-                dr[tr] += fabs(d0);
-                dst[0] = make_double2(d0, __dsub_rn(v[tr + 1][1], v[tr][1]));
+                dst[0] = make_double2(__dsub_rn(v[tr + 1][0], v[tr][0]), __dsub_rn(v[tr + 1][1], v[tr][1]));
                 dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
             }
         }
-    } else if (PCC) {
-        // the records are written by greedy_delta_kernel next to this kernel; only the drift bounds are needed here
-        // (same terms, same order as above)
-        for (int t = c.gtid; t < nt; t += c.gth) {
-            double v[QA_NFMT];
-#pragma unroll
-            for (int f = 0; f < QA_NFMT; ++f) v[f] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], 0) * nt + t] : 0.0;
-#pragma unroll
-            for (int tr = 0; tr + 1 < QA_NFMT; ++tr)
-                if (tr + 1 < ord.n) dr[tr] += fabs(__dsub_rn(v[tr + 1], v[tr]));
-        }
     }
-#pragma unroll
-    for (int tr = 0; tr + 1 < QA_NFMT; ++tr)
-        if (PCC && tr + 1 < ord.n) dr[tr] = c_reduce_d<false>(c, dr[tr]);
     if (c.gtid == 0) {
 #pragma unroll
-        for (int tr = 0; tr + 1 < QA_NFMT; ++tr) hdr[11 + tr] = dr[tr];
+        for (int tr = 0; tr + 1 < QA_NFMT; ++tr) hdr[11 + tr] = dr_sum[tr];
         hdr[0] = sx; hdr[1] = sx2; hdr[2] = S[0]; hdr[3] = S[1]; hdr[4] = S[2]; hdr[5] = S[3];
         hdr[6] = (double)degraded;
         hdr[7] = (double)(clock64() - t_start);
