@@ -506,20 +506,29 @@ def test_batch_graph_replay_equals_eager(qa):
     shapes = [(256, 512), (96, 320), (512, 256)]
     xs = [synthetic.randn_bf16_cpu(s, 40 + i) for i, s in enumerate(shapes)]
     xs2 = [synthetic.randn_bf16_cpu(s, 50 + i) for i, s in enumerate(shapes)]
-    b = GreedyBatch(shapes, metric="pcc", threshold=0.999, seed=9)
-    for data in (xs, xs2):
-        b.load_device(data)
-        b.run()
-        eager = b.collect()
-        for s in b.slots:
-            s["assignment"].fill_(-1)
-            s["counts"].zero_()
-        b.run_graph()
-        graph = b.collect()
-        for e, g in zip(eager, graph):
-            assert np.array_equal(e["assignment"], g["assignment"])
-            assert e["counts"] == g["counts"]
-            assert np.array_equal(e["state"][:8], g["state"][:8])
+    eng = qa["engine"]
+    for metric, thr, fmts in (("pcc", 0.999, list(G.MIXED)), ("mae", 3e-4, list(G.MIXED)), ("pcc", 0.9995, ["bfp8", "bfp4"]),
+                              ("atol", 2e-3, list(G.MIXED))):
+        b = GreedyBatch(shapes + [shapes[0]], metric=metric, threshold=thr, seed=9, tile_formats=fmts)   # two tensors share a tile count
+        for data in (xs, xs2):
+            b.load_device(data + [data[0]])
+            b.run()
+            eager = b.collect()
+            for s in b.slots:
+                s["assignment"].fill_(-1)
+                s["counts"].zero_()
+            b.run_graph()
+            graph = b.collect()
+            for e, g in zip(eager, graph):
+                assert np.array_equal(e["assignment"], g["assignment"]), (metric, fmts)
+                assert e["counts"] == g["counts"]
+                assert np.array_equal(e["state"][:8], g["state"][:8])
+            assert np.array_equal(graph[0]["assignment"], graph[3]["assignment"])        # the follower of a shared prefetch
+            # and against the single-call engine path on the first tensor
+            p = eng.prepare_tiles(data[0].cuda())
+            table = eng.tile_stats(p, G.MIXED, exact_abs=(metric == "mae"))
+            a1, c1, _ = eng.greedy_assign(table, p.numel, metric, thr, fmts, eng.make_rng(9))
+            assert np.array_equal(a1.cpu().numpy().reshape(graph[0]["assignment"].shape), graph[0]["assignment"]), (metric, fmts)
 
 
 def test_batch_from_host_async_equals_sync(qa):
