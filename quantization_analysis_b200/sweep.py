@@ -45,3 +45,19 @@ def sweep_tensor(x, tile_formats=MIXED_TILE_FORMATS, metric: str = "pcc", steps:
         rows.append(row)
         prev, prev_row = maps[i], row
     return rows, maps
+
+
+def write_sweep_csv(out_dir, rows, formats=MIXED_TILE_FORMATS):
+    """``sweep_results.csv`` in the reference's layout (scripts/sweep_mixed_tile_threshold.py:792-797):
+    step,threshold,size_bytes,pcc,mae,atol,<fmt>_tiles..."""
+    from pathlib import Path
+    out = Path(out_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    headers = ["step", "threshold", "size_bytes", "pcc", "mae", "atol", *[f"{fmt}_tiles" for fmt in formats]]
+    with (out / "sweep_results.csv").open("w", encoding="utf-8") as f:
+        f.write(",".join(headers) + "\n")
+        for i, r in enumerate(rows):
+            vals = {"step": i, "threshold": float(r["threshold"]), "size_bytes": r["total_bytes"], "pcc": r["pcc"], "mae": r["mae"],
+                    "atol": r["atol"], **{f"{fmt}_tiles": r["counts"].get(fmt, 0) for fmt in formats}}
+            f.write(",".join(str(vals.get(h, "")) for h in headers) + "\n")
+    return out / "sweep_results.csv"

@@ -550,3 +550,32 @@ def test_batch_from_host_async_equals_sync(qa):
     b0.run()
     for w, g in zip(want, b0.collect()):
         assert np.array_equal(w["assignment"], g["assignment"]) and w["counts"] == g["counts"]
+
+
+def test_reconstruct_from_saved_assignment_and_sweep_csv(qa, tmp_path):
+    """reconstruct.py (scripts/reconstruct_mixed_tile_assignment.py) and the sweep CSV writer on a golden case."""
+    import json
+    from quantization_analysis_b200 import reconstruct, sweep, wq
+    x = G.algo_input("het_256x512")
+    rng = np.random.default_rng(3)
+    p_th, p_tw = x.shape[0] // 32, x.shape[1] // 32
+    a = rng.integers(0, 4, size=(p_th, p_tw)).astype(np.int8)
+    wq.write_assignment(tmp_path, "mixed_tile_greedy", "t.weight", a)
+    d = tmp_path / "mixed_tile_greedy" / wq._slug("t.weight")
+    fm = reconstruct.load_mapping(d / "assignment_mapping.json")
+    y = reconstruct.reconstruct_from_assignment(x, np.load(d / "assignment.npy"), fm)
+    want = orc.apply_assignment(x, a)
+    assert np.array_equal(y.view(np.uint32), want.view(np.uint32))
+    # a permuted mapping names the same formats through different integers
+    perm = ["bfp2", "bf16", "bfp4", "bfp8"]
+    a2 = np.vectorize(lambda v: perm.index(list(G.MIXED)[v]))(a).astype(np.int8)
+    y2 = reconstruct.reconstruct_from_assignment(x, a2, perm)
+    assert np.array_equal(y2.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(ValueError):
+        reconstruct.reconstruct_from_assignment(x, a[:-1], fm)
+    rows, _maps = sweep.sweep_tensor(x, metric="pcc", steps=5, lowest=0.9)
+    path = sweep.write_sweep_csv(tmp_path / "sweep", rows)
+    lines = path.read_text().strip().splitlines()
+    assert lines[0] == "step,threshold,size_bytes,pcc,mae,atol,bf16_tiles,bfp8_tiles,bfp4_tiles,bfp2_tiles"
+    assert len(lines) == 6 and lines[1].split(",")[0] == "0"
+    assert sum(int(v) for v in lines[3].split(",")[6:]) == p_th * p_tw
