@@ -68,6 +68,11 @@ const char* qa_last_error(void);
 int qa_quant_recon(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
                    uint32_t fmt_mask, void* const out[QA_NFMT], qa_stream_t stream);
 
+/* mxfp4 (which = 0) / nvfp4 (which = 1) scalar proxies: the elementwise maps quantize_weight_values applies for these two
+ * formats (quantization_formats.py:171-183; simulate_mxfp4_amax / simulate_nvfp4_amax :254-278 on a block of identical
+ * values).  x: bf16 or float32 [n]; out: float32 [n]. */
+int qa_scalar_proxy(const void* x, int x_dtype, int64_t n, int which, float* out, qa_stream_t stream);
+
 /* Fused quantize + per-tile reconstruction-error statistics (one read of x).
  * Replaces the per-tile sums of mixed_tile_greedy.py:135-220,245-254 and feeds the tensor-level
  * metrics of wq:684-687 / mixed_tile_random.py:135-141.  vec_tail: 0, or for a 1-D input laid

@@ -118,7 +118,82 @@ def quantize(x: np.ndarray, fmt: str) -> np.ndarray:
         return bfp_quantize(x, MANT_BITS[f])
     if f == "fp0":
         return np.zeros_like(x, dtype=np.float32)
+    if f == "mxfp4":
+        return scalar_proxy(x, "mxfp4")
+    if f == "nvfp4":
+        return scalar_proxy(x, "nvfp4")
     raise ValueError(f"Unsupported weight format: {f}")
+
+
+# --------------------------------------------------------------------------- #
+# mxfp4 / nvfp4 scalar proxies (quantization_formats.py:171-183, 197-278)
+# --------------------------------------------------------------------------- #
+_FP4_LEVELS = np.array([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], dtype=np.float32)
+
+
+def _fp4_nearest(a: np.ndarray) -> np.ndarray:
+    """quantize_fp4_e2m1 on non-negative float32 (:197-202): first argmin of the float32 |a - level|."""
+    d = np.abs(a[..., None] - _FP4_LEVELS[None, :])
+    return _FP4_LEVELS[np.argmin(d, axis=-1)]
+
+
+def _exponent_f32(a: np.ndarray) -> np.ndarray:
+    """floor(log2(a)) for positive finite float32, exactly (the reference takes np.log2 in float32, whose rounding can
+    differ for an argument within ~|k| * 4e-8 of a power of two 2^k; never the case for the quotients of bf16 values)."""
+    m, e = np.frexp(a.astype(np.float64))
+    return (e - 1).astype(np.int32)
+
+
+def _fp8_e4m3(ax: np.ndarray) -> np.ndarray:
+    """quantize_fp8_e4m3 on non-negative float32 (:205-251)."""
+    out = np.zeros_like(ax, dtype=np.float32)
+    nz = ax > 0
+    if not nz.any():
+        return out
+    a = ax[nz]
+    e = _exponent_f32(a)
+    res = np.zeros_like(a, dtype=np.float32)
+    normal, sub, big = (e >= -6) & (e <= 7), e < -6, e > 7          # e_min = 1 - bias = -6, e_max = 14 - bias = 7
+    if normal.any():
+        en = e[normal].astype(np.int64)
+        m = a[normal].astype(np.float64) / (2.0 ** en)
+        fq = np.round((m - 1.0) * 8.0) / 8.0
+        bumped = fq >= 1.0
+        fq = np.where(bumped, 0.0, fq)
+        en = np.where(bumped, np.minimum(en + 1, 7), en)
+        res[normal] = ((1.0 + fq) * (2.0 ** en)).astype(np.float32)
+    if sub.any():
+        step = np.float32(2.0 ** -9)
+        res[sub] = np.round(a[sub] / step) * step
+    if big.any():
+        res[big] = np.float32(240.0)                                        # (1 + 7/8) * 2^7
+    out[nz] = res
+    return out
+
+
+def scalar_proxy(x: np.ndarray, fmt: str) -> np.ndarray:
+    """Elementwise mxfp4 / nvfp4 proxy: every magnitude is treated as the amax of a block of identical values."""
+    x = np.asarray(x, dtype=np.float32)
+    ax = np.abs(x).reshape(-1)
+    q = np.zeros_like(ax)
+    fin = np.isfinite(ax) & (ax > 0)
+    a = ax[fin]
+    with np.errstate(all="ignore"):
+        if fmt == "mxfp4":
+            s = (a.astype(np.float64) / 6.0).astype(np.float32)            # python-float division, then float32 (:256-257)
+            ok = s > 0
+            m, e = np.frexp(s.astype(np.float64))
+            k = np.where(m == 0.5, e - 1, e).astype(np.float64)           # ceil(log2(s))
+            sq = np.where(ok, np.exp2(k), 0.0).astype(np.float32)
+        else:
+            s = a / np.float32(6.0)                                        # float32 division (:266)
+            sq = _fp8_e4m3(s)
+            ok = sq > 0
+        r = np.zeros_like(a)
+        r[ok] = _fp4_nearest(a[ok] / sq[ok]) * sq[ok]
+    q[fin] = r
+    q[~np.isfinite(ax)] = np.nan                                            # inf / nan propagate as nan
+    return (np.sign(x).reshape(-1) * q).reshape(x.shape).astype(np.float32)
 
 
 # --------------------------------------------------------------------------- #

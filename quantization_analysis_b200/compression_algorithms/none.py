@@ -13,21 +13,23 @@ def quantize_all(xf, formats) -> dict:
     """{fmt: reconstruction} for every requested format with a single read of xf."""
     is_t = isinstance(xf, torch.Tensor)
     fmts = [f.lower() for f in formats]
+    proxies = ("mxfp4", "nvfp4")                      # elementwise scalar proxies: their own kernel (qa_scalar_proxy)
     for f in fmts:
-        if f in ("mxfp4", "nvfp4"):
-            raise NotImplementedError(f"format '{f}' is outside the accelerated path")
-        if f not in engine.FMT_INDEX and f != "fp0":
+        if f not in engine.FMT_INDEX and f != "fp0" and f not in proxies:
             raise ValueError(f"Unsupported weight format: {f}")
     n = int(xf.numel()) if is_t else int(np.asarray(xf).size)
     out = {}
     if n == 0:
         for f in fmts:
-            out[f] = xf.to(torch.bfloat16) if is_t else np.asarray(xf, dtype=np.float32)
+            out[f] = xf.to(torch.float32 if f in proxies else torch.bfloat16) if is_t else np.asarray(xf, dtype=np.float32)
         return out
     p = engine.prepare_rows(xf)
     recon = engine.quant_recon(p, [f for f in fmts if f in engine.FMT_INDEX])
     for f in fmts:
-        if f == "fp0":
+        if f in proxies:
+            from ..quantization_formats import quantize_weight_values
+            out[f] = quantize_weight_values(xf, f)
+        elif f == "fp0":
             out[f] = (torch.zeros(p.shape, dtype=torch.bfloat16, device=p.data.device) if is_t
                       else np.zeros(p.shape, dtype=np.float32))
         elif is_t:

@@ -4,6 +4,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <algorithm>
+
 #include "qa_common.cuh"
 
 namespace qa {
@@ -322,6 +324,91 @@ extern "C" int qa_apply_assignment(const void* x, int x_dtype, int64_t rows, int
         else apply_kernel<QA_DT_F32, false><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, tiles_w, assignment, out_bf16);
     } else { set_error("qa_apply_assignment: bad dtype"); return 1; }
     return check_launch("qa_apply_assignment");
+}
+
+// ---------------------------------------------------------------------------------------------
+// mxfp4 / nvfp4 scalar proxies (quantization_formats.py:171-183 with :197-278): every magnitude is treated as the amax
+// of a block of identical values, so the result is an elementwise function of |x|:
+//   mxfp4: s = float32(|x| / 6.0 in float64), s_q = 2^ceil(log2 s), q = fp4_e2m1(|x| / s_q) * s_q
+//   nvfp4: s = |x| / 6 (float32),             s_q = fp8_e4m3(s),   q = fp4_e2m1(|x| / s_q) * s_q   (0 when s_q == 0)
+// in the reference's float32 arithmetic (IEEE division, first-argmin level search, round-half-even).  floor / ceil of
+// log2 are taken from the exponent field, i.e. exactly; the reference's float32 np.log2 can round an argument within
+// ~|k| * 4e-8 of 2^k onto k - never the case for quotients of bf16 values.
+// ---------------------------------------------------------------------------------------------
+namespace qa {
+
+__device__ __forceinline__ float fp4_e2m1_nearest(float a) {        // a >= 0 (or nan); first argmin of |a - level|
+    const float L[8] = {0.f, 0.5f, 1.f, 1.5f, 2.f, 3.f, 4.f, 6.f};
+    float best = fabsf(__fsub_rn(a, 0.f)), lv = 0.f;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        const float d = fabsf(__fsub_rn(a, L[i]));
+        if (d < best) { best = d; lv = L[i]; }
+    }
+    return lv;
+}
+
+__device__ __forceinline__ float fp8_e4m3_pos(float ax) {            // ax > 0, finite (quantization_formats.py:205-251)
+    const uint32_t u = __float_as_uint(ax);
+    const int eb = (int)(u >> 23);
+    const int e = eb ? eb - 127 : -127;                              // floor(log2 ax); subnormals only need "< -6"
+    if (e > 7) return 240.f;                                         // (1 + 7/8) * 2^7
+    if (e < -6) return __fmul_rn(rintf(__fmul_rn(ax, 512.f)), 0.001953125f);     // round(ax / 2^-9) * 2^-9
+    const float m = __fmul_rn(ax, __uint_as_float((uint32_t)(127 - e) << 23));    // ax / 2^e in [1, 2), exact
+    float fq = __fmul_rn(rintf(__fmul_rn(__fsub_rn(m, 1.f), 8.f)), 0.125f);
+    int en = e;
+    if (fq >= 1.f) { fq = 0.f; en = min(e + 1, 7); }
+    return __fmul_rn(__fadd_rn(1.f, fq), __uint_as_float((uint32_t)(127 + en) << 23));
+}
+
+template <int DT, int WHICH>
+__global__ void __launch_bounds__(256) scalar_proxy_kernel(const void* __restrict__ x, int64_t n, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const float v = DT == QA_DT_BF16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(x)[i] << 16)
+                                         : reinterpret_cast<const float*>(x)[i];
+        const float am = fabsf(v);
+        float q = 0.f;
+        if (!(am <= 3.402823466e38f)) {                              // inf / nan propagate as nan
+            out[i] = __uint_as_float(0x7FC00000u);
+            continue;
+        }
+        if (am > 0.f) {
+            float sq = 0.f;
+            if (WHICH == 0) {
+                const float s = __double2float_rn((double)am / 6.0);
+                if (s > 0.f) {
+                    const uint32_t u = __float_as_uint(s), mant = u & 0x7FFFFFu;
+                    const int eb = (int)(u >> 23);
+                    int k;                                           // ceil(log2 s)
+                    if (eb) k = eb - 127 + (mant ? 1 : 0);
+                    else { const int p = 31 - __clz((int)mant); k = -149 + p + ((mant & (mant - 1u)) ? 1 : 0); }
+                    sq = k >= -126 ? __uint_as_float((uint32_t)(k + 127) << 23) : __uint_as_float(1u << (k + 149));
+                }
+            } else {
+                const float s = __fdiv_rn(am, 6.f);
+                if (s > 0.f) sq = fp8_e4m3_pos(s);
+            }
+            if (sq > 0.f) q = __fmul_rn(fp4_e2m1_nearest(__fdiv_rn(am, sq)), sq);
+        }
+        out[i] = v > 0.f ? q : (v < 0.f ? -q : 0.f);
+    }
+}
+
+}  // namespace qa
+
+extern "C" int qa_scalar_proxy(const void* x, int x_dtype, int64_t n, int which, float* out, qa_stream_t stream) {
+    if (n < 0 || (n > 0 && (!x || !out)) || (which != 0 && which != 1)) { set_error("qa_scalar_proxy: bad args"); return 1; }
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(n, 256), 148 * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_dtype == QA_DT_BF16) {
+        if (which == 0) scalar_proxy_kernel<QA_DT_BF16, 0><<<grid, 256, 0, s>>>(x, n, out);
+        else scalar_proxy_kernel<QA_DT_BF16, 1><<<grid, 256, 0, s>>>(x, n, out);
+    } else if (x_dtype == QA_DT_F32) {
+        if (which == 0) scalar_proxy_kernel<QA_DT_F32, 0><<<grid, 256, 0, s>>>(x, n, out);
+        else scalar_proxy_kernel<QA_DT_F32, 1><<<grid, 256, 0, s>>>(x, n, out);
+    } else { set_error("qa_scalar_proxy: bad dtype"); return 1; }
+    return check_launch("qa_scalar_proxy");
 }
 
 extern "C" int qa_f32_to_bf16_checked(const float* x, int64_t n, void* out_bf16,

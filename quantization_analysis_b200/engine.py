@@ -154,6 +154,13 @@ def tile_stats(p: Prepared, formats=MIXED_FORMATS, strict: bool | None = None, e
     return table
 
 
+def scalar_proxy(x: torch.Tensor, which: int, out: torch.Tensor) -> torch.Tensor:
+    """mxfp4 (0) / nvfp4 (1) scalar proxy of a contiguous bf16 / float32 device tensor into a float32 tensor."""
+    code = _lib.QA_DT_BF16 if x.dtype == torch.bfloat16 else _lib.QA_DT_F32
+    check(_lib.lib().qa_scalar_proxy(_ptr(x), code, x.numel(), int(which), _ptr(out), _stream()), "qa_scalar_proxy")
+    return out
+
+
 def tile_scores(p: Prepared, formats=MIXED_FORMATS) -> torch.Tensor:
     """float32 [3 metrics, NFMT, ntiles] NumPy-faithful padded-tile scores."""
     s = torch.zeros((3, NFMT, p.ntiles), dtype=torch.float32, device=p.data.device)

@@ -82,6 +82,25 @@ def quantize_weight_values(x, fmt: str):
     if fmt == "fp0":
         return quantize_fp0(x)
     if fmt in ("mxfp4", "nvfp4"):
-        raise NotImplementedError(
-            f"format '{fmt}' (scalar proxy, quantization_formats.py:174-183) is outside the accelerated path")
+        return _scalar_proxy(x, fmt)
     raise ValueError(f"Unsupported weight format: {fmt}")
+
+
+def _scalar_proxy(x, fmt: str):
+    """mxfp4 / nvfp4 scalar proxies (:171-183): elementwise on the device (qa_scalar_proxy), float32 out."""
+    which = 0 if fmt == "mxfp4" else 1
+    if _is_torch(x):
+        xd = x.contiguous()
+        if xd.dtype not in (torch.bfloat16, torch.float32):
+            xd = xd.to(torch.float32)
+        out = torch.empty(xd.shape, dtype=torch.float32, device=xd.device)
+        if xd.numel():
+            engine.scalar_proxy(xd, which, out)
+        return out
+    xn = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    if xn.size == 0:
+        return xn.astype(np.float32)
+    xd = torch.from_numpy(xn.reshape(-1)).to(engine._require_cuda())
+    out = torch.empty_like(xd)
+    engine.scalar_proxy(xd, which, out)
+    return out.cpu().numpy().reshape(xn.shape)

@@ -201,7 +201,26 @@ def make_rng() -> None:
     print("numpy_rng.npz:", len(out))
 
 
+def make_scalar_proxies() -> None:
+    """mxfp4 / nvfp4 scalar proxies (quantization_formats.py:171-183): every bf16 bit pattern and 20 000 random float32
+    values over 32 octaves, through the reference's per-element Python loop."""
+    x16 = (np.arange(65536, dtype=np.uint32) << 16).view(np.float32)
+    rng = np.random.default_rng(5)
+    xr = (rng.standard_normal(20000) * np.exp2(rng.integers(-20, 12, 20000))).astype(np.float32)
+    out = {"rand__in": bits(xr)}
+    with np.errstate(all="ignore"):
+        for fmt in ("mxfp4", "nvfp4"):
+            out[f"bf16__{fmt}"] = bits(ref_qf.quantize_weight_values(x16, fmt))
+            out[f"rand__{fmt}"] = bits(ref_qf.quantize_weight_values(xr, fmt))
+    np.savez_compressed(HERE / "scalar_proxies.npz", **out)
+    print("scalar_proxies.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "scalar_proxies":
+        make_scalar_proxies()
+        raise SystemExit(0)
+    make_scalar_proxies()
     make_kats()
     make_rng()
     make_algos()

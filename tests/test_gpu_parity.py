@@ -579,3 +579,39 @@ def test_reconstruct_from_saved_assignment_and_sweep_csv(qa, tmp_path):
     assert lines[0] == "step,threshold,size_bytes,pcc,mae,atol,bf16_tiles,bfp8_tiles,bfp4_tiles,bfp2_tiles"
     assert len(lines) == 6 and lines[1].split(",")[0] == "0"
     assert sum(int(v) for v in lines[3].split(",")[6:]) == p_th * p_tw
+
+
+def test_scalar_proxies_match_reference_goldens_on_device(qa):
+    """qa_scalar_proxy (mxfp4 / nvfp4) vs the reference on every bf16 pattern (bf16 and float32 inputs) and on 20 000
+    random float32 values."""
+    import torch
+    from quantization_analysis_b200 import quantization_formats as qf
+    z = G.npz("scalar_proxies.npz")
+    u16 = np.arange(65536, dtype=np.uint32)
+    x16 = (u16 << 16).view(np.float32)
+    xb = torch.from_numpy(u16.astype(np.int32).astype(np.int16)).view(torch.bfloat16).cuda()
+    xr = z["rand__in"].view(np.float32)
+    for fmt in ("mxfp4", "nvfp4"):
+        w16 = z[f"bf16__{fmt}"]
+        nan = np.isnan(w16.view(np.float32))
+        for got in (qf.quantize_weight_values(x16, fmt), qf.quantize_weight_values(xb, fmt).cpu().numpy()):
+            assert got.dtype == np.float32
+            assert np.array_equal(np.isnan(got), nan), fmt
+            assert np.array_equal(got.view(np.uint32)[~nan], w16[~nan]), fmt
+        gr = qf.quantize_weight_values(xr.reshape(100, 200), fmt)
+        assert gr.shape == (100, 200)
+        assert np.array_equal(gr.reshape(-1).view(np.uint32), z[f"rand__{fmt}"]), fmt
+    assert qf.quantize_weight_values(np.zeros((0, 4), np.float32), "mxfp4").shape == (0, 4)
+
+
+def test_none_compression_with_wq_default_formats(qa):
+    """NoneCompression over wq's default format list (mxfp4, nvfp4 first: hf_model_utils.py:317-319) vs the oracle."""
+    from quantization_analysis_b200 import compression_algorithms as ca
+    x = G.algo_input("het_256x512")
+    fmts = ["mxfp4", "nvfp4", "bf16", "bfp8", "bfp4", "bfp2", "fp0"]
+    res = ca.create_algorithm("none", {}).run(x, fmts, None, None)
+    assert [r.fmt for r in res] == [f.upper() for f in fmts]
+    for r, f in zip(res, fmts):
+        with np.errstate(all="ignore"):
+            want = orc.quantize(x, f)
+        assert np.array_equal(np.asarray(r.y, dtype=np.float32).view(np.uint32), want.view(np.uint32)), f

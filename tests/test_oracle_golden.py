@@ -117,3 +117,18 @@ def test_pcg64_restatement_matches_numpy_streams():
     assert np.array_equal(r.integers(2, 777), z["s123__int2_777"])
     assert np.array_equal(r.permutation(2), z["s123__perm_2"])
     assert np.array_equal(r.permutation(1), z["s123__perm_1"])
+
+
+def test_scalar_proxies_match_reference_goldens():
+    """mxfp4 / nvfp4 scalar proxies: oracle vs the reference on every bf16 pattern and 20 000 random float32 values."""
+    z = G.npz("scalar_proxies.npz")
+    x16 = (np.arange(65536, dtype=np.uint32) << 16).view(np.float32)
+    xr = z["rand__in"].view(np.float32)
+    for fmt in ("mxfp4", "nvfp4"):
+        with np.errstate(all="ignore"):
+            got16, gotr = orc.quantize(x16, fmt), orc.quantize(xr, fmt)
+        w16 = z[f"bf16__{fmt}"]
+        nan = np.isnan(w16.view(np.float32))
+        assert np.array_equal(np.isnan(got16), nan)
+        assert np.array_equal(got16.view(np.uint32)[~nan], w16[~nan]), fmt
+        assert np.array_equal(gotr.view(np.uint32), z[f"rand__{fmt}"]), fmt
