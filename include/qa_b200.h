@@ -73,6 +73,14 @@ int qa_quant_recon(const void* x, int x_dtype, int64_t rows, int64_t cols, int64
  * values).  x: bf16 or float32 [n]; out: float32 [n]. */
 int qa_scalar_proxy(const void* x, int x_dtype, int64_t n, int which, float* out, qa_stream_t stream);
 
+/* fp8 e4m3fn weights + per-block inverse scales -> float32 (and / or bf16 patterns), the step in front of the path for
+ * real checkpoints: hf_model_utils.py:199-215 (_dequantize_tensor_with_scale_inv), block = ceil(shape / scale shape).
+ * w_fp8: uint8 [rows, cols]; scale_inv: float32 [scale_rows, scale_cols]; out_f32 / out_bf16: either may be NULL;
+ * *inexact_count (device, may be NULL) = products that are not bf16-exact (then the float32 kernels must be used). */
+int qa_fp8_block_dequant(const void* w_fp8, const float* scale_inv, int64_t rows, int64_t cols,
+                         int64_t scale_rows, int64_t scale_cols, float* out_f32, void* out_bf16,
+                         unsigned long long* inexact_count, qa_stream_t stream);
+
 /* Fused quantize + per-tile reconstruction-error statistics (one read of x).
  * Replaces the per-tile sums of mixed_tile_greedy.py:135-220,245-254 and feeds the tensor-level
  * metrics of wq:684-687 / mixed_tile_random.py:135-141.  vec_tail: 0, or for a 1-D input laid

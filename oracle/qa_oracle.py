@@ -811,3 +811,35 @@ def wq_scores(x: np.ndarray, y: np.ndarray) -> dict:
     y = np.asarray(y, dtype=np.float32)
     diff = np.abs(x - y)
     return {"mae": float(np.mean(diff)), "atol": float(np.max(diff)), "pcc": pearson_f32(x, y)}
+
+
+# --------------------------------------------------------------------------- #
+# fp8 e4m3fn block dequantization (hf_model_utils.py:199-215, used at :266-281): the step in front of the path
+# --------------------------------------------------------------------------- #
+def fp8_e4m3fn_table() -> np.ndarray:
+    """float32 value of each of the 256 e4m3fn bit patterns (bias 7, no inf, 0x7f / 0xff = nan)."""
+    out = np.zeros(256, dtype=np.float32)
+    for b in range(256):
+        sgn = -1.0 if b & 0x80 else 1.0
+        e, m = (b >> 3) & 0xF, b & 7
+        if e == 15 and m == 7:
+            v = np.nan
+        elif e == 0:
+            v = sgn * m * 2.0 ** -9
+        else:
+            v = sgn * (1.0 + m / 8.0) * 2.0 ** (e - 7)
+        out[b] = v
+    out[0x80] = -0.0
+    return out
+
+
+def fp8_block_dequant(w_bits: np.ndarray, scale_inv: np.ndarray) -> np.ndarray:
+    """tensor.float() * inv_scale.repeat_interleave(block)[:rows, :cols] with block = ceil(shape / scale shape), float32."""
+    w = np.asarray(w_bits, dtype=np.uint8)
+    sc = np.asarray(scale_inv, dtype=np.float32)
+    assert w.ndim == 2 and sc.ndim == 2
+    br = max(1, -(-w.shape[0] // sc.shape[0])) if sc.shape[0] > 0 else 1
+    bc = max(1, -(-w.shape[1] // sc.shape[1])) if sc.shape[1] > 0 else 1
+    full = np.repeat(np.repeat(sc, br, axis=0), bc, axis=1)[: w.shape[0], : w.shape[1]]
+    with np.errstate(all="ignore"):
+        return (fp8_e4m3fn_table()[w] * full).astype(np.float32)

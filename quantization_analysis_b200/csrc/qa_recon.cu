@@ -411,6 +411,63 @@ extern "C" int qa_scalar_proxy(const void* x, int x_dtype, int64_t n, int which,
     return check_launch("qa_scalar_proxy");
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp8 e4m3fn + per-block inverse scale -> float32 (hf_model_utils.py:199-215: tensor.float() * inv_scale over
+// ceil(shape / scale shape) blocks), the step in front of the path for real checkpoints.  Also emits the bf16 pattern of
+// every product and counts the products that are not bf16-exact, so the caller can pick the bf16 or the float32 kernels
+// without another pass (qa_f32_to_bf16_checked fused in).
+// ---------------------------------------------------------------------------------------------
+namespace qa {
+
+__device__ __forceinline__ float e4m3fn_to_f32(uint32_t b) {
+    const uint32_t sgn = (b & 0x80u) << 24, e = (b >> 3) & 0xFu, m = b & 7u;
+    if (e == 15u && m == 7u) return __uint_as_float(0x7FC00000u);
+    if (e == 0u) return __uint_as_float(sgn | __float_as_uint((float)m * 0.001953125f));      // m * 2^-9
+    return __uint_as_float(sgn | ((e + 120u) << 23) | (m << 20));
+}
+
+__global__ void __launch_bounds__(256) fp8_block_dequant_kernel(const uint8_t* __restrict__ w, const float* __restrict__ scale,
+                                                                int64_t rows, int64_t cols, int64_t scols, int64_t br, int64_t bc,
+                                                                float* __restrict__ out, uint16_t* __restrict__ out_bf16,
+                                                                unsigned long long* __restrict__ inexact) {
+    unsigned long long bad = 0;
+    const int64_t n = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / cols, c = i - r * cols;
+        float v = __fmul_rn(e4m3fn_to_f32(w[i]), scale[(r / br) * scols + c / bc]);
+        if (v != v) v = __uint_as_float(0x7FC00000u);                 // one nan pattern (bf16-exact: not counted)
+        if (out) out[i] = v;
+        const uint32_t u = __float_as_uint(v);
+        if (out_bf16) out_bf16[i] = (uint16_t)(bf16_rne_bits(u) >> 16);
+        bad += (u & 0xFFFFu) != 0u;
+    }
+    if (inexact) {
+        bad = __reduce_add_sync(0xFFFFFFFFu, (unsigned)bad);
+        if ((threadIdx.x & 31) == 0 && bad) atomicAdd(inexact, bad);
+    }
+}
+
+}  // namespace qa
+
+extern "C" int qa_fp8_block_dequant(const void* w_fp8, const float* scale_inv, int64_t rows, int64_t cols, int64_t scale_rows,
+                                    int64_t scale_cols, float* out_f32, void* out_bf16, unsigned long long* inexact_count,
+                                    qa_stream_t stream) {
+    if (rows < 0 || cols < 0 || scale_rows <= 0 || scale_cols <= 0 || !w_fp8 || !scale_inv || (!out_f32 && !out_bf16)) {
+        set_error("qa_fp8_block_dequant: bad args");
+        return 1;
+    }
+    if (rows == 0 || cols == 0) return 0;
+    const int64_t br = std::max<int64_t>(1, cdiv(rows, scale_rows)), bc = std::max<int64_t>(1, cdiv(cols, scale_cols));
+    if (cdiv(rows, br) > scale_rows || cdiv(cols, bc) > scale_cols) { set_error("qa_fp8_block_dequant: scale shape too small"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (inexact_count && cudaMemsetAsync(inexact_count, 0, sizeof(unsigned long long), s) != cudaSuccess)
+        return check_launch("qa_fp8_block_dequant (memset)");
+    const unsigned grid = (unsigned)std::min<int64_t>(cdiv(rows * cols, 256), 148 * 32);
+    fp8_block_dequant_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(w_fp8), scale_inv, rows, cols, scale_cols, br, bc,
+                                                  out_f32, reinterpret_cast<uint16_t*>(out_bf16), inexact_count);
+    return check_launch("qa_fp8_block_dequant");
+}
+
 extern "C" int qa_f32_to_bf16_checked(const float* x, int64_t n, void* out_bf16,
                                       unsigned long long* inexact_count, qa_stream_t stream) {
     if (n < 0 || !inexact_count) { set_error("qa_f32_to_bf16_checked: bad args"); return 1; }

@@ -154,6 +154,24 @@ def tile_stats(p: Prepared, formats=MIXED_FORMATS, strict: bool | None = None, e
     return table
 
 
+def fp8_block_dequant(w_fp8: torch.Tensor, scale_inv: torch.Tensor, want_bf16: bool = True):
+    """fp8 e4m3fn [rows, cols] (uint8 or float8_e4m3fn storage) * scale_inv blocks -> (float32 tensor, bf16 tensor or None,
+    number of products that are not bf16-exact).  hf_model_utils.py:199-215 on the device."""
+    dev = _require_cuda()
+    w = w_fp8.to(dev).contiguous()
+    w8 = w.view(torch.uint8) if w.dtype != torch.uint8 else w
+    sc = scale_inv.to(dev, torch.float32).contiguous()
+    if w8.dim() != 2 or sc.dim() != 2:
+        raise ValueError("fp8_block_dequant expects 2-D weight and scale tensors")
+    rows, cols = w8.shape
+    out = torch.empty((rows, cols), dtype=torch.float32, device=dev)
+    ob = torch.empty((rows, cols), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    check(_lib.lib().qa_fp8_block_dequant(_ptr(w8), _ptr(sc), rows, cols, sc.shape[0], sc.shape[1], _ptr(out), _ptr(ob), _ptr(cnt),
+                                          _stream()), "qa_fp8_block_dequant")
+    return out, ob, int(cnt.item())
+
+
 def scalar_proxy(x: torch.Tensor, which: int, out: torch.Tensor) -> torch.Tensor:
     """mxfp4 (0) / nvfp4 (1) scalar proxy of a contiguous bf16 / float32 device tensor into a float32 tensor."""
     code = _lib.QA_DT_BF16 if x.dtype == torch.bfloat16 else _lib.QA_DT_F32

@@ -216,10 +216,36 @@ def make_scalar_proxies() -> None:
     print("scalar_proxies.npz:", len(out), "arrays")
 
 
+def make_fp8_dequant() -> None:
+    """hf_model_utils._dequantize_tensor_with_scale_inv on every e4m3fn pattern and on a ragged 300x520 tensor with
+    128x128 blocks (scale shape 3x5), through torch's float8_e4m3fn."""
+    import torch
+    import hf_model_utils as ref_hf
+    rng = np.random.default_rng(11)
+    out = {}
+    allb = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    s1 = np.array([[0.0123456]], dtype=np.float32)
+    out["all__w"], out["all__s"] = allb, s1
+    out["all__out"] = bits(ref_hf._dequantize_tensor_with_scale_inv(torch.from_numpy(allb).view(torch.float8_e4m3fn),
+                                                                    torch.from_numpy(s1)).numpy())
+    w = rng.integers(0, 256, size=(300, 520), dtype=np.uint8)
+    w[(w & 0x7F) == 0x7F] = 0x3A                                  # no nan patterns in the random block
+    s2 = (np.exp2(rng.uniform(-14, -8, size=(3, 5))) * rng.uniform(1, 2, size=(3, 5))).astype(np.float32)
+    out["rag__w"], out["rag__s"] = w, s2
+    out["rag__out"] = bits(ref_hf._dequantize_tensor_with_scale_inv(torch.from_numpy(w).view(torch.float8_e4m3fn),
+                                                                    torch.from_numpy(s2)).numpy())
+    np.savez_compressed(HERE / "fp8_dequant.npz", **out)
+    print("fp8_dequant.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "scalar_proxies":
         make_scalar_proxies()
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fp8_dequant":
+        make_fp8_dequant()
+        raise SystemExit(0)
+    make_fp8_dequant()
     make_scalar_proxies()
     make_kats()
     make_rng()

@@ -615,3 +615,26 @@ def test_none_compression_with_wq_default_formats(qa):
         with np.errstate(all="ignore"):
             want = orc.quantize(x, f)
         assert np.array_equal(np.asarray(r.y, dtype=np.float32).view(np.uint32), want.view(np.uint32)), f
+
+
+def test_fp8_block_dequant_matches_reference_goldens_on_device(qa):
+    """qa_fp8_block_dequant vs hf_model_utils._dequantize_tensor_with_scale_inv (goldens through torch's float8_e4m3fn):
+    float32 products bit-equal, bf16 patterns = RNE of them, inexact count = products with non-zero low bits."""
+    import torch
+    eng = qa["engine"]
+    z = G.npz("fp8_dequant.npz")
+    for tag in ("all", "rag"):
+        w, s = z[f"{tag}__w"], z[f"{tag}__s"]
+        out, ob, cnt = eng.fp8_block_dequant(torch.from_numpy(w), torch.from_numpy(s))
+        got = out.cpu().numpy()
+        want = z[f"{tag}__out"].view(np.float32).reshape(got.shape)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan]), tag
+        fin = want[~nan]
+        assert cnt == int(((want.view(np.uint32) & 0xFFFF) != 0).sum())
+        assert np.array_equal(ob.float().cpu().numpy()[~nan].view(np.uint32), orc.bf16_round(fin).view(np.uint32))
+    # a power-of-two scale keeps every product bf16-exact: the bf16 kernels apply
+    w = z["rag__w"]
+    out, ob, cnt = eng.fp8_block_dequant(torch.from_numpy(w).view(torch.float8_e4m3fn), torch.full((3, 5), 2.0 ** -7))
+    assert cnt == 0 and torch.equal(ob.float(), out)

@@ -132,3 +132,14 @@ def test_scalar_proxies_match_reference_goldens():
         assert np.array_equal(np.isnan(got16), nan)
         assert np.array_equal(got16.view(np.uint32)[~nan], w16[~nan]), fmt
         assert np.array_equal(gotr.view(np.uint32), z[f"rand__{fmt}"]), fmt
+
+
+def test_fp8_block_dequant_matches_reference_goldens():
+    """fp8 e4m3fn + scale_inv block dequantization (hf_model_utils.py:199-215): oracle vs the reference through torch."""
+    z = G.npz("fp8_dequant.npz")
+    for tag in ("all", "rag"):
+        got = orc.fp8_block_dequant(z[f"{tag}__w"], z[f"{tag}__s"])
+        want = z[f"{tag}__out"].view(np.float32).reshape(got.shape)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got), nan)
+        assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan]), tag
