@@ -638,3 +638,27 @@ def test_fp8_block_dequant_matches_reference_goldens_on_device(qa):
     w = z["rag__w"]
     out, ob, cnt = eng.fp8_block_dequant(torch.from_numpy(w).view(torch.float8_e4m3fn), torch.full((3, 5), 2.0 ** -7))
     assert cnt == 0 and torch.equal(ob.float(), out)
+
+
+def test_batch_degenerate_inputs_match_oracle(qa):
+    """The staged batch schedule (graph replay) on the degenerate tensors - den == 0 branches, all-zero tables, one tile,
+    a non-zero mean, tiny values, ragged tiles - against the CPU oracle, for pcc and mae."""
+    import torch
+    from quantization_analysis_b200.batch import GreedyBatch
+    rng = np.random.default_rng(3)
+    xs = [np.full((96, 128), 0.25, dtype=np.float32), np.zeros((64, 96), dtype=np.float32),
+          (rng.standard_normal((32, 32)) * 0.02).astype(np.float32),
+          (1.0 + rng.standard_normal((256, 384)) * 0.01).astype(np.float32),
+          (rng.standard_normal((128, 256)) * 1e-30).astype(np.float32),
+          (rng.standard_normal((130, 75)) * 0.02).astype(np.float32)]
+    xs = [torch.from_numpy(x).to(torch.bfloat16) for x in xs]
+    shapes = [tuple(x.shape) for x in xs]
+    for metric, thr in (("pcc", 0.999), ("pcc", 0.9), ("mae", 1e-4)):
+        b = GreedyBatch(shapes, metric=metric, threshold=thr, seed=5)
+        b.load_device(xs)
+        b.run_graph()
+        for x, r in zip(xs, b.collect()):
+            xf = x.float().numpy()
+            want, counts = orc.greedy_assign(orc.tile_stat_table(xf), list(G.MIXED), metric, thr, 5)
+            assert np.array_equal(r["assignment"], want), (metric, thr, xf.shape)
+            assert r["counts"] == counts
