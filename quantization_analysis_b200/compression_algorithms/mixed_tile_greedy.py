@@ -52,8 +52,11 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
         if seed == 0:
             seed = secrets.randbits(31)           # mixed_tile_greedy.py:222-224
         rng = engine.make_rng(seed, p.data.device)
-        assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng,
-                                                             parallel=False if self.sequential else None)
+        if self.sequential or self.metric == "atol":
+            assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng,
+                                                                 parallel=False if self.sequential else None)
+        else:   # stages overlapped on side streams: same bits, about half the latency
+            assignment, counts_dev, state = engine.greedy_assign_staged(table, p.numel, self.metric, self.threshold, tile_formats, rng)
         counts = mc.counts_dict(counts_dev)
         sums = engine.assignment_sums(table, assignment)
         metrics = engine.metrics_from_sums(sums.cpu().numpy(), p.numel)

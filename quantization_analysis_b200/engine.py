@@ -287,6 +287,68 @@ def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float
     return assignment, counts, state
 
 
+_STAGE_STREAMS: dict = {}
+
+
+def greedy_assign_staged(table: torch.Tensor, numel: int, metric: str, threshold: float, fmt_order, rng: torch.Tensor):
+    """greedy_assign for one tensor with the stages overlapped on side streams: the data-independent permutations
+    (qa_perm_resolve_chain / qa_perm_resolve / qa_perm_apply) next to the initial sums and delta records
+    (qa_greedy_init_sums / qa_greedy_init_deltas), then the chain by pass range (qa_greedy_assign_passes).
+    Same outputs, bit for bit, as greedy_assign; about half its latency on a large tensor.  `rng` is advanced."""
+    if metric not in ("pcc", "mae") or len(fmt_order) < 2:
+        return greedy_assign(table, numel, metric, threshold, fmt_order, rng)
+    L = _lib.lib()
+    dev = table.device
+    nt, nf = table.shape[1], len(fmt_order)
+    three = nf >= 3
+    key = (dev.index, "stage")
+    if key not in _STAGE_STREAMS:
+        _STAGE_STREAMS[key] = (torch.cuda.Stream(device=dev, priority=-1), torch.cuda.Stream(device=dev, priority=-1))
+    side, side2 = _STAGE_STREAMS[key]
+    cur = torch.cuda.current_stream(dev)
+    order = _lib.int32_array([FMT_INDEX[f] for f in fmt_order])
+    assignment = torch.empty(nt, dtype=torch.int8, device=dev)
+    counts = torch.zeros(NFMT, dtype=torch.int64, device=dev)
+    state = torch.zeros(24, dtype=torch.float64, device=dev)
+    work = torch.empty(L.qa_greedy_par_work_bytes(nt), dtype=torch.uint8, device=dev)
+    init = torch.empty(L.qa_greedy_init_bytes(nt), dtype=torch.uint8, device=dev)
+    jarr = torch.empty((3, nt), dtype=torch.int32, device=dev)
+    pre_order = torch.empty((2, nt), dtype=torch.int32, device=dev)
+    rngs = torch.stack([rng, rng, rng]).contiguous()
+    awork = torch.empty((2, L.qa_perm_apply_work_bytes(nt)), dtype=torch.uint8, device=dev)
+    ev2, ev_a2, ev_a3 = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+    side.wait_stream(cur)
+    side2.wait_stream(cur)
+    check(L.qa_perm_resolve_chain(_ptr(rng), nt, 2, 0b10, _ptr(jarr), _ptr(rngs), side.cuda_stream), "qa_perm_resolve_chain")
+    if three:
+        ev2.record(side)
+        side2.wait_event(ev2)
+        check(L.qa_perm_apply(_ptr(jarr[1]), nt, None, _ptr(pre_order[0]), _ptr(awork[0]), side2.cuda_stream), "qa_perm_apply")
+        ev_a2.record(side2)
+        check(L.qa_perm_resolve(_ptr(rngs[1]), nt, _ptr(jarr[2]), _ptr(rngs[2]), side.cuda_stream), "qa_perm_resolve")
+        check(L.qa_perm_apply(_ptr(jarr[2]), nt, None, _ptr(pre_order[1]), _ptr(awork[1]), side.cuda_stream), "qa_perm_apply")
+        ev_a3.record(side)
+    else:
+        check(L.qa_perm_apply(_ptr(jarr[1]), nt, None, _ptr(pre_order[0]), _ptr(awork[0]), side.cuda_stream), "qa_perm_apply")
+        ev_a2.record(side)
+    iargs = (_ptr(table), nt, METRIC_CODE[metric], order, nf, _ptr(init))
+    check(L.qa_greedy_init_deltas(*iargs, _stream()), "qa_greedy_init_deltas")
+    check(L.qa_greedy_init_sums(*iargs, _stream()), "qa_greedy_init_sums")
+    pargs = (_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, nf, _ptr(rng), _ptr(assignment),
+             _ptr(counts), _ptr(state), _ptr(work), _ptr(pre_order), _ptr(rngs[1]), _ptr(init))
+    cur.wait_event(ev_a2)
+    if three:
+        check(L.qa_greedy_assign_passes(*pargs, 0, 2, _stream()), "qa_greedy_assign_passes")
+        cur.wait_event(ev_a3)
+        check(L.qa_greedy_assign_passes(*pargs, 2, nf, _stream()), "qa_greedy_assign_passes")
+    else:
+        check(L.qa_greedy_assign_passes(*pargs, 0, nf, _stream()), "qa_greedy_assign_passes")
+    for t in (work, init, jarr, pre_order, rngs, awork):       # buffers used on side streams: keep them until `cur` is past
+        t.record_stream(side)
+        t.record_stream(side2)
+    return assignment, counts, state
+
+
 def threshold_assign(scores_metric: torch.Tensor, order_fmts, is_pcc: bool, thresholds) -> tuple[torch.Tensor, torch.Tensor]:
     """scores_metric float32 [NFMT, ntiles]; thresholds: iterable of floats (cast to float32 like NumPy 2).
     -> (assignment int8 [nthr, ntiles], counts int64 [nthr, 4])."""

@@ -662,3 +662,23 @@ def test_batch_degenerate_inputs_match_oracle(qa):
             want, counts = orc.greedy_assign(orc.tile_stat_table(xf), list(G.MIXED), metric, thr, 5)
             assert np.array_equal(r["assignment"], want), (metric, thr, xf.shape)
             assert r["counts"] == counts
+
+
+def test_greedy_assign_staged_single_tensor_equals_inline(qa):
+    """engine.greedy_assign_staged (side-stream prefetch + init + chain by pass range for ONE tensor - what
+    MixedTileGreedyCompression.run uses) == engine.greedy_assign, including the stream position."""
+    import torch
+    eng = qa["engine"]
+    x = G.algo_input("het_256x512")
+    p = eng.prepare_tiles(x)
+    for metric, thr, fmts in (("pcc", 0.995, list(G.MIXED)), ("mae", 3e-4, list(G.MIXED)), ("pcc", 0.9999, ["bfp4", "bfp2"]),
+                              ("pcc", 0.99999, list(G.MIXED)), ("atol", 2e-3, list(G.MIXED))):
+        table = eng.tile_stats(p, G.MIXED, exact_abs=True)
+        r1, r2 = eng.make_rng(31), eng.make_rng(31)
+        a1, c1, s1 = eng.greedy_assign(table, p.numel, metric, thr, fmts, r1)
+        for _ in range(2):                                   # twice: the side streams are reused
+            r2 = eng.make_rng(31)
+            a2, c2, s2 = eng.greedy_assign_staged(table, p.numel, metric, thr, fmts, r2)
+            torch.cuda.synchronize()
+            assert torch.equal(a1, a2) and torch.equal(c1, c2) and torch.equal(r1, r2), (metric, thr, fmts)
+            assert torch.equal(s1[:8], s2[:8])
