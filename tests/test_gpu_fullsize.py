@@ -123,3 +123,30 @@ def test_striped_greedy_over_nccl_two_gpus():
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "striped_greedy_ok" in out.stdout
+
+
+def test_greedy_cluster_sizes_agree_fullsize():
+    """The cluster kernels give the one-thread chain's map, counts, sums and stream position for every cluster size
+    (qa_greedy_cluster_cap 1, 2, 4, 8 and the automatic 16) on a 36 864-tile and a 114 688-tile tensor, single call and staged."""
+    from quantization_analysis_b200 import _lib, engine as eng, synthetic
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    fmts = list(eng.MIXED_FORMATS)
+    for shape, seed in (((24576, 1536), 21), ((7168, 16384), 22)):
+        x = synthetic.device_randn_bf16(shape, seed, dev)
+        p = eng.prepare_tiles(x)
+        table = eng.tile_stats(p, fmts, exact_abs=False)
+        r0 = eng.make_rng(123)
+        a0, c0, s0 = eng.greedy_assign(table, p.numel, "pcc", 0.999, fmts, r0, parallel=False)
+        try:
+            for cap in (1, 2, 4, 8, 0):
+                L.qa_greedy_cluster_cap(cap)
+                for staged in (False, True):
+                    r = eng.make_rng(123)
+                    fn = eng.greedy_assign_staged if staged else eng.greedy_assign
+                    a, c, s = fn(table, p.numel, "pcc", 0.999, fmts, r)
+                    torch.cuda.synchronize()
+                    assert torch.equal(a, a0) and torch.equal(c, c0) and torch.equal(r, r0), (shape, cap, staged)
+                    assert int(s[12].item()) == (cap if cap else (16 if p.ntiles >= 65536 else 8))
+        finally:
+            L.qa_greedy_cluster_cap(0)
