@@ -241,6 +241,10 @@ int qa_apply_assignment(const void* x, int x_dtype, int64_t rows, int64_t cols, 
  * {sx, sx2, sy, sy2, sxy, sabs, max_abs, 0}.  Feeds wq:684-687-style scoring. */
 int qa_assignment_sums(const double* table, int64_t ntiles, const int8_t* assignment, int fmt,
                        double* out, qa_stream_t stream);
+/* qa_assignment_sums for nmaps assignment maps at once (one block per map): maps int8 [nmaps][ntiles] -> out double
+ * [nmaps][8].  The sweep (scripts/sweep_mixed_tile_threshold.py:700-760) scores every threshold's map with one launch. */
+int qa_assignment_sums_batch(const double* table, int64_t ntiles, const int8_t* maps, int nmaps,
+                             double* out, qa_stream_t stream);
 
 /* Sums over two arbitrary float32 arrays for compression_algorithms/metrics.py:6-27 (pearson_corr, mae, atol) and
  * the whole-tensor scoring of wq:684-687: out double[8] = {sum a, sum a^2, sum b, sum b^2, sum a*b, sum |a-b|,

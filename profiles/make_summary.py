@@ -71,7 +71,12 @@ md += ["Reading.  `stats_fast_kernel`: DRAM traffic equals the algorithmic bytes
        "| `apply_fast_kernel` | final MIXED reconstruction from a tile map (4 B/elem) | 0.085 ms | 5505 | 0.84 |",
        "| `stats_fast_kernel` | quantize + tile statistics (2.17 B/elem) | 0.144 ms | 1772 | 0.27 |",
        "| `tile_scores_kernel` | NumPy-float32-faithful tile scores, 4 formats x 3 metrics (threshold / sweep) | 0.72 ms | 327 (input) | 0.05 |",
-       "| greedy kernels | o_proj, 114 688 tiles, 4 passes: resolve x3 224 us + 2 x apply 34 us (side streams), init sums 119 us, chain 235 us | - | - | latency-bound |"]
+       "| greedy kernels | o_proj, 114 688 tiles, 4 passes: resolve x3 224 us + 2 x apply 34 us (side streams), init sums 119 us, chain 235 us | - | - | latency-bound |",
+       "", "## Other configurations (device-resident, `profiles/cfg3_breakdown.py`, `profiles/cfg5_throughput.py`)", "",
+       "* cfg3 threshold sweep, 32 thresholds, o_proj-size tensor: 1.61 ms = 146 GB/s of bf16 weights (tile_scores 0.75 ms, tile_stats 0.19 ms,",
+       "  threshold_assign 0.14 ms, all 32 maps scored by one `qa_assignment_sums_batch` launch).",
+       "* cfg5 share of one GPU (96 experts x 3 = 288 tensors of 14 336 tiles, 8.46 GB): 6.8 ms = 1239 GB/s (shared permutations, 32 streams,",
+       "  clusters capped at 2 CTAs)."]
 open("profiles/r1_summary.md", "w").write("\n".join(md) + "\n")
 for f in (f"bench_{tag}.json", f"launches_{tag}.csv", f"{tag}_raw.csv"):
     shutil.copy(g + f, "profiles/" + f)

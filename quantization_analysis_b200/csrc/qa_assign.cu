@@ -340,11 +340,14 @@ constexpr int SB = 1024;
 __global__ void __launch_bounds__(SB) assignment_sums_kernel(const double* __restrict__ table, int64_t nt,
                                                              const int8_t* __restrict__ assignment, int fmt,
                                                              double* __restrict__ out) {
+    // one block per assignment map: block b reduces map b (maps are [gridDim.x][nt]) into out[b][8]
+    if (assignment) assignment += (int64_t)blockIdx.x * nt;
+    out += (int64_t)blockIdx.x * 8;
     __shared__ double sm[7][SB / 32];
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    const int64_t per = cdiv(nt, (int64_t)SB);
-    const int64_t t0 = min(nt, (int64_t)threadIdx.x * per), t1 = min(nt, t0 + per);
-    for (int64_t t = t0; t < t1; ++t) {
+    // thread t takes tiles t, t + SB, ...: coalesced column reads, and a fixed (deterministic) summation shape
+#pragma unroll 2
+    for (int64_t t = threadIdx.x; t < nt; t += SB) {
         int c = assignment ? (int)assignment[t] : fmt;
         v[0] += table[QA_STAT_SX * nt + t];
         v[1] += table[QA_STAT_SX2 * nt + t];
@@ -524,6 +527,14 @@ extern "C" int qa_random_samples(const double* table, int64_t ntiles, double num
         rc = check_launch("qa_random_samples(skip)");
     }
     return rc;
+}
+
+extern "C" int qa_assignment_sums_batch(const double* table, int64_t ntiles, const int8_t* maps, int nmaps, double* out,
+                                        qa_stream_t stream) {
+    if (!table || ntiles <= 0 || !maps || nmaps < 0 || (nmaps > 0 && !out)) { set_error("qa_assignment_sums_batch: bad args"); return 1; }
+    if (nmaps == 0) return 0;
+    assignment_sums_kernel<<<(unsigned)nmaps, SB, 0, (cudaStream_t)stream>>>(table, ntiles, maps, -1, out);
+    return check_launch("qa_assignment_sums_batch");
 }
 
 extern "C" int qa_assignment_sums(const double* table, int64_t ntiles, const int8_t* assignment, int fmt,

@@ -400,6 +400,15 @@ def assignment_sums(table: torch.Tensor, assignment: torch.Tensor | None = None,
     return out
 
 
+def assignment_sums_batch(table: torch.Tensor, maps: torch.Tensor) -> torch.Tensor:
+    """Whole-tensor sums of every row of `maps` (int8 [nmaps, ntiles]) in one launch -> float64 [nmaps, 8]."""
+    m = maps.to(torch.int8).contiguous()
+    out = torch.zeros((m.shape[0], 8), dtype=torch.float64, device=table.device)
+    check(_lib.lib().qa_assignment_sums_batch(_ptr(table), table.shape[1], _ptr(m), m.shape[0], _ptr(out), _stream()),
+          "qa_assignment_sums_batch")
+    return out
+
+
 def pair_sums(a, b=None) -> tuple[np.ndarray, int]:
     """{sum a, sum a^2, sum b, sum b^2, sum ab, sum|a-b|, max|a-b|} over two arrays (b=None: zeros), float64."""
     dev = _require_cuda()

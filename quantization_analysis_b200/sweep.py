@@ -34,16 +34,13 @@ def sweep_tensor(x, tile_formats=MIXED_TILE_FORMATS, metric: str = "pcc", steps:
     order = formats_by_precision(tile_formats)
     maps, counts = engine.threshold_assign(scores, order, metric == "pcc", thresholds)
     counts = counts.cpu().numpy()
-    rows, prev, prev_row = [], None, None
+    sums = engine.assignment_sums_batch(table, maps).cpu().numpy()     # every threshold's map scored in one launch
+    rows = []
     for i, thr in enumerate(thresholds):
-        if prev is not None and torch.equal(maps[i], prev):       # unchanged assignment: reuse (sweep:736-742)
-            row = dict(prev_row, threshold=float(thr))
-        else:
-            m = engine.metrics_from_sums(engine.assignment_sums(table, maps[i]).cpu().numpy(), p.numel)
-            c = {f: int(counts[i, j]) for j, f in enumerate(MIXED_TILE_FORMATS)}
-            row = {"threshold": float(thr), "counts": c, "total_bytes": mixed_tile_total_bytes(c), **m}
-        rows.append(row)
-        prev, prev_row = maps[i], row
+        # (the reference reuses the previous row when the assignment did not change, sweep:736-742: same numbers)
+        m = engine.metrics_from_sums(sums[i], p.numel)
+        c = {f: int(counts[i, j]) for j, f in enumerate(MIXED_TILE_FORMATS)}
+        rows.append({"threshold": float(thr), "counts": c, "total_bytes": mixed_tile_total_bytes(c), **m})
     return rows, maps
 
 
