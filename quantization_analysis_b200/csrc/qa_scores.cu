@@ -91,10 +91,22 @@ __global__ void __launch_bounds__(SC_WARPS * 32) tile_scores_kernel(
         eaa = __fmaf_rn(am[r], am[r], eaa);
         oaa = __fmaf_rn(am[r + 1], am[r + 1], oaa);
     }
-    const float na = __fsqrt_rn(sdot_fold(eaa, oaa, lane));
+    const float daa = sdot_fold(eaa, oaa, lane);
+    const float na = __fsqrt_rn(daa);
 
     for (int f = 0; f < QA_NFMT; ++f) {
         if (!((fmt_mask >> f) & 1u)) continue;
+        if (DT == QA_DT_BF16 && f == 0) {
+            // bf16 of a bf16-exact tile is the tile itself: b == a, so every intermediate of pearson_corr repeats a's
+            // (dot(a-m, b-m) = ||a-m||^2, nb = na) and mae = atol = 0; metrics.py:14-15 for a zero denominator
+            const float denom = __fmul_rn(na, na);
+            if (lane == 0) {
+                scores[(QA_METRIC_PCC * QA_NFMT + f) * ntiles + t] = denom == 0.f ? 1.f : __fdiv_rn(daa, denom);
+                scores[(QA_METRIC_MAE * QA_NFMT + f) * ntiles + t] = 0.f;
+                scores[(QA_METRIC_ATOL * QA_NFMT + f) * ntiles + t] = 0.f;
+            }
+            continue;
+        }
         __syncwarp();
         for (int g = lane; g < 64; g += 32) {
             const int r = g >> 1, c0 = (g & 1) * GROUP;
