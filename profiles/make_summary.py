@@ -73,8 +73,8 @@ md += ["Reading.  `stats_fast_kernel`: DRAM traffic equals the algorithmic bytes
        "| `tile_scores_kernel` | NumPy-float32-faithful tile scores, 4 formats x 3 metrics (threshold / sweep) | 0.72 ms | 327 (input) | 0.05 |",
        "| greedy kernels | o_proj, 114 688 tiles, 4 passes: resolve x3 224 us + 2 x apply 34 us (side streams), init sums 119 us, chain 235 us | - | - | latency-bound |",
        "", "## Other configurations (device-resident, `profiles/cfg3_breakdown.py`, `profiles/cfg5_throughput.py`)", "",
-       "* cfg3 threshold sweep, 32 thresholds, o_proj-size tensor: 1.61 ms = 146 GB/s of bf16 weights (tile_scores 0.75 ms, tile_stats 0.19 ms,",
-       "  threshold_assign 0.14 ms, all 32 maps scored by one `qa_assignment_sums_batch` launch).",
+       "* cfg3 threshold sweep, 32 thresholds, o_proj-size tensor: 1.40 ms = 167 GB/s of bf16 weights (tile_scores 0.63 ms, tile_stats 0.18 ms,",
+       "  threshold_assign 0.12 ms, all 32 maps scored by one `qa_assignment_sums_batch` launch).",
        "* cfg5 share of one GPU (96 experts x 3 = 288 tensors of 14 336 tiles, 8.46 GB): 6.8 ms = 1239 GB/s (shared permutations, 32 streams,",
        "  clusters capped at 2 CTAs)."]
 open("profiles/r1_summary.md", "w").write("\n".join(md) + "\n")
