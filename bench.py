@@ -291,6 +291,20 @@ def main() -> None:
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_value = world * nbytes * K / e2e_s / 1e9
+    # the ceiling of that number: a plain pinned-host -> device copy of the same bytes (the PCIe link of this GPU)
+    big = max(range(len(host)), key=lambda i: host[i].numel())
+    dst = torch.empty_like(host[big], device=dev)
+    for _ in range(2):
+        dst.copy_(host[big], non_blocking=True)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        dst.copy_(host[big], non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_copy_gbs = 5 * host[big].numel() * 2 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del dst
     if world > 1:                                   # per-tensor result rows to rank 0 (tiny)
         rows = [[r["metrics"]["pcc"], r["metrics"]["mae"], r["metrics"]["atol"]] for r in res_e2e]
         gathered = [None] * world if rank == 0 else None
@@ -349,6 +363,7 @@ def main() -> None:
                 "dtype": "bf16 in; f32 group-scaled + f64 sums", "data": "synthetic", "config": config_dict(world),
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": batch.d2h_bytes(),
+                        "h2d_copy_gbs": h2d_copy_gbs,
                         "api": "GreedyBatch.enqueue_from_host(pinned bf16 host tensors) / finish() -> assignment maps + pcc/mae/atol on host, two batches alternating"},
                 "gpu_launches": batch.launches_per_step * K,
                 "step_latency_ms": ms_single,
