@@ -238,7 +238,32 @@ def make_fp8_dequant() -> None:
     print("fp8_dequant.npz:", len(out), "arrays")
 
 
+def make_cfg2() -> None:
+    """The bench workload itself (configs[1], rank 0): the reference's mixed-tile-greedy pcc >= 0.999, seed 123, on the five
+    layer-0 self_attn shapes with bench.py's synthetic bf16 tensors (seed 1000 + i).  Full size: 187 M elements, minutes."""
+    import time
+    arrays, meta = {}, {}
+    quantizer = Quantizer(backend="emulation")
+    for i, name in enumerate(synthetic.ATTN_NAMES):
+        shape = synthetic.DEEPSEEK_R1_SHAPES[name]
+        x = synthetic.randn_bf16_cpu(shape, 1000 + i).float().numpy()
+        t0 = time.time()
+        g = create_algorithm("mixed-tile-greedy", {"metric": "pcc", "threshold": 0.999, "seed": 123})
+        res = g.run(xf=x, formats=FORMATS, quantizer=quantizer, cache=None)[0]
+        a = np.asarray(res.meta["assignment"], dtype=np.int8)
+        key = name.split(".")[-2]
+        arrays[key] = a
+        meta[key] = {"name": name, "shape": list(shape), "seed": 1000 + i, "input_sha256": sha(x), "counts": res.tile_counts,
+                     "tile_bytes": res.tile_bytes, "assignment_sha256": sha(a), "reference_seconds": round(time.time() - t0, 1)}
+        print("cfg2", key, meta[key]["counts"], meta[key]["reference_seconds"], "s", flush=True)
+    np.savez_compressed(HERE / "cfg2_bench_workload.npz", **arrays)
+    (HERE / "cfg2_bench_workload.json").write_text(json.dumps(meta, indent=1))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg2":
+        make_cfg2()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "scalar_proxies":
         make_scalar_proxies()
         raise SystemExit(0)

@@ -182,3 +182,34 @@ def test_heavy_tailed_fullsize_fast_stats_and_staged_greedy():
         b.run_graph()
         r = b.collect()[0]
         assert np.array_equal(r["assignment"].reshape(-1), a0.cpu().numpy())
+
+
+def test_cfg2_bench_workload_equals_reference_maps():
+    """The bench workload at full size (187 M elements) against the UNMODIFIED reference: tests/golden/cfg2_bench_workload.*
+    hold the reference's mixed-tile-greedy maps (pcc >= 0.999, seed 123) for bench.py's five synthetic tensors; the batched,
+    staged, graph-replayed schedule reproduces every map bit for bit, from device-resident and from host inputs."""
+    import json
+    import hashlib
+    from pathlib import Path
+    import numpy as np
+    from quantization_analysis_b200 import synthetic
+    from quantization_analysis_b200.batch import GreedyBatch
+    gold = Path(__file__).resolve().parent / "golden"
+    meta = json.loads((gold / "cfg2_bench_workload.json").read_text())
+    maps = dict(np.load(gold / "cfg2_bench_workload.npz"))
+    names = synthetic.ATTN_NAMES
+    shapes = [synthetic.DEEPSEEK_R1_SHAPES[n] for n in names]
+    host = [synthetic.randn_bf16_cpu(s, 1000 + i).pin_memory() for i, s in enumerate(shapes)]
+    b = GreedyBatch(shapes, metric="pcc", threshold=0.999, seed=123)
+    b.load_device(host)
+    b.run_graph()
+    res_dev = b.collect()
+    res_host = b.run_from_host(host)
+    for n, rd, rh in zip(names, res_dev, res_host):
+        key = n.split(".")[-2]
+        want = maps[key]
+        for r in (rd, rh):
+            assert np.array_equal(r["assignment"], want), key
+            assert r["counts"] == {k: int(v) for k, v in meta[key]["counts"].items()}, key
+            assert hashlib.sha256(np.ascontiguousarray(r["assignment"].astype(np.int8)).tobytes()).hexdigest() == meta[key]["assignment_sha256"]
+        assert r["metrics"]["pcc"] >= 0.999
