@@ -173,6 +173,23 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def maps_vs_reference_goldens(items, *result_sets):
+    """Rank 0's tensors are the ones tests/golden/cfg2_bench_workload.* holds the UNMODIFIED reference's greedy maps for
+    (made by tests/golden/make_golden.py cfg2): compare the maps this run produced - device-resident and end-to-end - with
+    them.  True / False, or None when the fixtures are not there."""
+    import numpy as np
+    gold = ROOT / "tests" / "golden" / "cfg2_bench_workload.npz"
+    if not gold.exists():
+        return None
+    maps = dict(np.load(gold))
+    ok = True
+    for results in result_sets:
+        for (name, _shape, _seed), r in zip(items, results):
+            key = name.split(".")[-2]
+            ok = ok and key in maps and bool(np.array_equal(r["assignment"], maps[key]))
+    return ok
+
+
 # --------------------------------------------------------------------------------------------
 def main() -> None:
     ap = argparse.ArgumentParser()
@@ -369,7 +386,8 @@ def main() -> None:
                 "step_latency_ms": ms_single,
                 "roofline": roofline, "roofline_by_kernel": kernels,
                 "pct_of_8TBs": 100.0 * value / world / 8000.0,
-                "result_check": {"counts_q_a_proj": results[0]["counts"], "pcc_q_a_proj": results[0]["metrics"]["pcc"]}}
+                "result_check": {"counts_q_a_proj": results[0]["counts"], "pcc_q_a_proj": results[0]["metrics"]["pcc"],
+                                 "maps_equal_reference": maps_vs_reference_goldens(items, results, res_e2e)}}
         if world == 1 and not args.no_cpu_baseline:
             # fresh interpreter (no CUDA context, no inherited thread pools), bounded by a timeout
             import subprocess
