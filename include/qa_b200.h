@@ -188,7 +188,12 @@ int qa_greedy_assign_passes(const double* table, int64_t ntiles, double numel, i
                             double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
                             int8_t* assignment, int64_t* counts, double* state, void* work,
                             const int32_t* pre_order, const qa_pcg64* pre_rng, const void* init,
-                            int pass_begin, int pass_end, qa_stream_t stream);
+                            int pass_begin, int pass_end, int flags, qa_stream_t stream);
+/* flags bit 0: the caller does not read *rng afterwards.  The reference creates its generator inside _compress and
+ * drops it on return (mixed_tile_greedy.py:222-225); when the last pass cannot accept any tile its visiting order is
+ * irrelevant, and with this flag its permutation is not drawn at all (*rng is then unspecified).  Maps, counts and
+ * sums are unaffected. */
+#define QA_GREEDY_SKIP_FINAL_STREAM 1
 int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric,
                              double threshold, const int32_t* fmt_order, int nfmt, qa_pcg64* rng,
                              int8_t* assignment, int64_t* counts, double* state, void* work,

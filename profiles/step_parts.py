@@ -52,7 +52,7 @@ def chain_passes(st, b0, e0):
     check(L.qa_greedy_assign_passes(s["table"].data_ptr(), n, float(s["numel"]), METRIC_CODE["pcc"], 0.999, b._order, 4,
                                     s["rng"].data_ptr(), s["assignment"].data_ptr(), s["counts"].data_ptr(), s["state"].data_ptr(),
                                     s["work"].data_ptr(), s["pre_order"].data_ptr(), s["rngs"][1].data_ptr(), s["init"].data_ptr(),
-                                    b0, e0, st.cuda_stream), "chain passes")
+                                    b0, e0, 0, st.cuda_stream), "chain passes")
 
 
 def timed(fn, reps=20):

@@ -87,7 +87,7 @@ def lib():
     L.qa_perm_apply_work_bytes.argtypes = [i64]
     L.qa_perm_apply_work_bytes.restype = i64
     L.qa_perm_apply.argtypes = [vp, i64, vp, vp, vp, vp]
-    L.qa_greedy_assign_passes.argtypes = [vp, i64, f64, i32, f64, C.POINTER(C.c_int32), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    L.qa_greedy_assign_passes.argtypes = [vp, i64, f64, i32, f64, C.POINTER(C.c_int32), i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     L.qa_greedy_init_bytes.argtypes = [i64]
     L.qa_greedy_init_bytes.restype = i64
     L.qa_greedy_init.argtypes = [vp, i64, i32, C.POINTER(C.c_int32), i32, vp, vp]

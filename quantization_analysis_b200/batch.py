@@ -225,20 +225,21 @@ class GreedyBatch:
                 pargs = args + (slot["pre_order"].data_ptr() if pre else None, slot["rngs"][1].data_ptr() if pre else None,
                                 slot["init"].data_ptr())
                 nf = len(self.tile_formats)
+                SKIP = 1          # QA_GREEDY_SKIP_FINAL_STREAM: nobody reads slot['rng'] after the run (the reference drops its generator too)
                 ld = self.slots[slot["leader"]]
                 if pre and nf >= 3:
                     # passes 0-1 only need permutation #2 (applied on side2 while #3 is still being drawn); the later
                     # passes wait for the speculative #3 (applied last on the leader's side stream)
                     stream.wait_stream(side2)                 # own seed copy (and, for a leader, apply #2)
                     stream.wait_event(ld["ev_a2"])
-                    check(L.qa_greedy_assign_passes(*pargs, 0, 2, sp), "qa_greedy_assign_passes")
+                    check(L.qa_greedy_assign_passes(*pargs, 0, 2, 0, sp), "qa_greedy_assign_passes")
                     stream.wait_event(ld["ev_a3"])
-                    check(L.qa_greedy_assign_passes(*pargs, 2, nf, sp), "qa_greedy_assign_passes")
+                    check(L.qa_greedy_assign_passes(*pargs, 2, nf, SKIP, sp), "qa_greedy_assign_passes")
                 else:
                     if pre:
                         stream.wait_stream(side2 if not lead else side)
                         stream.wait_event(ld["ev_a2"])
-                    check(L.qa_greedy_assign_passes(*pargs, 0, nf, sp), "qa_greedy_assign_passes")
+                    check(L.qa_greedy_assign_passes(*pargs, 0, nf, SKIP, sp), "qa_greedy_assign_passes")
             mark("chain")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`
                 check(L.qa_assignment_sums(slot["table"].data_ptr(), slot["ntiles"], slot["assignment"].data_ptr(), -1,

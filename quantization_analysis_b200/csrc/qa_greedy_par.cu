@@ -1371,7 +1371,7 @@ template <bool PCC>
 __global__ void __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
                                                         int64_t* counts, double* state, ParWork w, int have_init, int fi_begin,
-                                                        int fi_end) {
+                                                        int fi_end, int flags) {
     // Passes [fi_begin, fi_end) of the format order.  A run may be split into several launches (so that a later pass can
     // wait for a prefetched permutation that an earlier one does not need); the running state travels in w.res.
     __shared__ Sh sh;
@@ -1528,7 +1528,9 @@ __global__ void __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS) greedy_par_kernel(con
             }
             if (none) {
                 if (PCC && relax_sy) S[0] = sb0_start;              // what an all-reject chain leaves behind
-                perm_resolve(c, g, m, nullptr);
+                // the permutation of an order-free pass only moves the stream; after the LAST pass nothing reads the
+                // stream any more unless the caller wants its final position (QA_GREEDY_SKIP_FINAL_STREAM)
+                if (!((flags & 1) && fi == ord.n - 1)) perm_resolve(c, g, m, nullptr);
                 for (int q = c.gtid; q < m; q += c.gth) w.fixed[cand ? cand[q] : q] = 1;
                 c.sync();
                 cyc_perm += clock64() - t_mark;
@@ -2008,7 +2010,7 @@ extern "C" int qa_greedy_init_deltas(const double* table, int64_t ntiles, int me
 extern "C" int qa_greedy_assign_passes(const double* table, int64_t ntiles, double numel, int metric, double threshold,
                                        const int32_t* fmt_order, int nfmt, qa_pcg64* rng, int8_t* assignment,
                                        int64_t* counts, double* state, void* work, const int32_t* pre_order,
-                                       const qa_pcg64* pre_rng, const void* init, int pass_begin, int pass_end,
+                                       const qa_pcg64* pre_rng, const void* init, int pass_begin, int pass_end, int flags,
                                        qa_stream_t stream) {
     if (pass_begin < 0 || pass_end <= pass_begin || pass_begin >= nfmt) { set_error("qa_greedy_assign_passes: bad pass range"); return 1; }
     if (!table || ntiles <= 0 || ntiles > 0x3FFFFFFF || !rng || !assignment || !counts || !state || !work) {
@@ -2028,9 +2030,9 @@ extern "C" int qa_greedy_assign_passes(const double* table, int64_t ntiles, doub
     }
     if (metric == QA_METRIC_PCC)
         return launch_cluster(greedy_par_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                              metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end);
+                              metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end, flags);
     return launch_cluster(greedy_par_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                          metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end);
+                          metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end, flags);
 }
 
 extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
@@ -2038,7 +2040,7 @@ extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, dou
                                         int64_t* counts, double* state, void* work, const int32_t* pre_order,
                                         const qa_pcg64* pre_rng, const void* init, qa_stream_t stream) {
     return qa_greedy_assign_passes(table, ntiles, numel, metric, threshold, fmt_order, nfmt, rng, assignment, counts, state, work,
-                                   pre_order, pre_rng, init, 0, nfmt, stream);
+                                   pre_order, pre_rng, init, 0, nfmt, 0, stream);
 }
 
 extern "C" int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric, double threshold,

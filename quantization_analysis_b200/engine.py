@@ -278,7 +278,7 @@ def greedy_assign(table: torch.Tensor, numel: int, metric: str, threshold: float
         for b, e in ranges:          # split_at: the same run as two launches (qa_greedy_assign_passes)
             check(L.qa_greedy_assign_passes(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order,
                                             len(fmt_order), _ptr(rng), _ptr(assignment), _ptr(counts), _ptr(state), _ptr(work),
-                                            _ptr(pre_order), _ptr(pre_rng), _ptr(init), b, e, _stream()), "qa_greedy_assign_par")
+                                            _ptr(pre_order), _ptr(pre_rng), _ptr(init), b, e, 0, _stream()), "qa_greedy_assign_par")
     else:
         work = torch.empty(L.qa_greedy_work_bytes(nt), dtype=torch.uint8, device=dev)
         check(L.qa_greedy_assign(_ptr(table), nt, float(numel), METRIC_CODE[metric], float(threshold), order, len(fmt_order),
@@ -338,11 +338,11 @@ def greedy_assign_staged(table: torch.Tensor, numel: int, metric: str, threshold
              _ptr(counts), _ptr(state), _ptr(work), _ptr(pre_order), _ptr(rngs[1]), _ptr(init))
     cur.wait_event(ev_a2)
     if three:
-        check(L.qa_greedy_assign_passes(*pargs, 0, 2, _stream()), "qa_greedy_assign_passes")
+        check(L.qa_greedy_assign_passes(*pargs, 0, 2, 0, _stream()), "qa_greedy_assign_passes")
         cur.wait_event(ev_a3)
-        check(L.qa_greedy_assign_passes(*pargs, 2, nf, _stream()), "qa_greedy_assign_passes")
+        check(L.qa_greedy_assign_passes(*pargs, 2, nf, 0, _stream()), "qa_greedy_assign_passes")
     else:
-        check(L.qa_greedy_assign_passes(*pargs, 0, nf, _stream()), "qa_greedy_assign_passes")
+        check(L.qa_greedy_assign_passes(*pargs, 0, nf, 0, _stream()), "qa_greedy_assign_passes")
     for t in (work, init, jarr, pre_order, rngs, awork):       # buffers used on side streams: keep them until `cur` is past
         t.record_stream(side)
         t.record_stream(side2)
