@@ -48,7 +48,7 @@ md += ["", "Round-1 history of the same bench: one-thread greedy 0.87 GB/s (415 
        "DSMEM exchange 141 -> cheaper collectives + prefetch of two permutations 298 -> prefetch / init / chain kernels, 32-byte delta",
        "records, speculative third permutation 412 -> one CUDA graph per step 477 -> order-free pass shortcut, EPS 8 531 -> chained",
        "resolve, serialized tile-stat passes, priority streams 658 -> pipelined table / init sums, split chain, two lists in flight 837",
-       "-> 256-thread cluster CTAs (tile-stat CTAs co-reside) ~920.",
+       "-> 256-thread cluster CTAs ~930 -> order-free last pass draws no permutation when the generator is dropped ~965.",
        "Stats kernel: 16 % -> 27 % (packed f32x2, xorsign clamp) -> 28-29 % (one CTA per 32x512 item).", "",
        "## ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`, same command; serialised and cold: compare shares)", ""] + L + ["",
        "## ncu --set full, first captured launch per kernel (o_proj 7168x16384 = 117.4 M elements)", ""]
@@ -62,8 +62,8 @@ md += ["Reading.  `stats_fast_kernel`: DRAM traffic equals the algorithmic bytes
        "CTAs per SM x 2/4/8 rows of loads in flight) confirms the shipped point.  The greedy kernels (`perm_resolve*`, `greedy_init_kernel`,",
        "`greedy_par_kernel`) are one cluster per tensor and latency-bound: their DRAM traffic is the 20 MB table plus 11 MB of delta records.",
        "A step's critical path is stats -> init sums -> chain of the largest tensor; `profiles/step_variants.py` prints the device-timestamp",
-       "timeline (o_proj alone: resolve 0-152 us | tile-stat 0-137 us | init sums over three table ranges 27-236 us -> chain passes 0-1",
-       "241-339 us -> passes 2-3 344-499 us).",
+       "timeline (o_proj alone: resolve 0-153 us | tile-stat 0-137 us | init sums over three table ranges 25-227 us -> chain passes 0-1",
+       "232-330 us -> passes 2-3 334-441 us).",
        "", "## Other kernels of the path (CUDA events, 10 launches each, o_proj-size tensor 7168x16384 unless noted)", "",
        "| kernel | what | time | algorithmic GB/s | fraction of copy peak |", "|---|---|---:|---:|---:|",
        "| `recon_fast_kernel` | cfg1 `none`: bfp8+bfp4+bfp2 reconstructions in one pass (8 B/elem) | 0.153 ms | 6123 | 0.94 |",
