@@ -652,14 +652,19 @@ __device__ __forceinline__ void consts_finish(Consts& c) {
     c.filter_ok = c.metric == QA_METRIC_PCC && c.thr > 0.0 && am2 > 0.0 && c.n > 0.0 && isfinite(c.K);
 }
 // mixed_tile_greedy.py:176-190 in Python-float order (no contraction); mx, n*mx and am2 are loop invariants
-__device__ __forceinline__ double pcc_value_par(const Consts& c, double sy, double sy2, double sxy, double sabs) {
-    if (c.n == 0.0) return 1.0;
-    const double my = __ddiv_rn(sy, c.n);
-    double bm2 = __dsub_rn(sy2, __dmul_rn(__dmul_rn(c.n, my), my));
+// (out of line: the division / square-root sequences are long and only run for near-ties and for the final report;
+// keeping them out of the decision loop keeps its instruction footprint small)
+__device__ __noinline__ double pcc_value_cold(double n, double am2, double nmx, double sy, double sy2, double sxy, double sabs) {
+    if (n == 0.0) return 1.0;
+    const double my = __ddiv_rn(sy, n);
+    double bm2 = __dsub_rn(sy2, __dmul_rn(__dmul_rn(n, my), my));
     if (bm2 < 0.0) bm2 = 0.0;
-    const double den = __dsqrt_rn(__dmul_rn(c.am2, bm2));
+    const double den = __dsqrt_rn(__dmul_rn(am2, bm2));
     if (den == 0.0) return sabs == 0.0 ? 1.0 : 0.0;
-    return __ddiv_rn(__dsub_rn(sxy, __dmul_rn(c.nmx, my)), den);
+    return __ddiv_rn(__dsub_rn(sxy, __dmul_rn(nmx, my)), den);
+}
+__device__ __forceinline__ double pcc_value_par(const Consts& c, double sy, double sy2, double sxy, double sabs) {
+    return pcc_value_cold(c.n, c.am2, c.nmx, sy, sy2, sxy, sabs);
 }
 __device__ __forceinline__ bool good_par(const Consts& c, const double (&S)[4]) {
     if (c.metric != QA_METRIC_PCC) {
