@@ -1372,7 +1372,7 @@ __global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restr
 #ifndef QA_CHAIN_MIN_BLOCKS
 #define QA_CHAIN_MIN_BLOCKS 1
 #endif
-template <bool PCC>
+template <bool PCC, bool INIT_INLINE>      // INIT_INLINE = false: the init phase ran ahead (greedy_init_kernel); its code is left out
 __global__ void __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
                                                         int64_t* counts, double* state, ParWork w, int have_init, int fi_begin,
@@ -1402,7 +1402,7 @@ __global__ void __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS) greedy_par_kernel(con
     const long long t_start = clock64();
 
     // ---- (1) initial sums, sequentially rounded in tile order (greedy_init_kernel ran ahead, or inline) ----
-    if (first && !have_init) {
+    if (INIT_INLINE && first && !have_init) {
         init_phase<PCC>(c, table, nt, ord, w.hdr, w.delta, true, 0, nt);
         c.sync();
     }
@@ -2033,11 +2033,14 @@ extern "C" int qa_greedy_assign_passes(const double* table, int64_t ntiles, doub
         pw.delta = const_cast<double*>(reinterpret_cast<const double*>(reinterpret_cast<const char*>(init) + al(8 * HDR_DOUBLES)));
         have_init = 1;
     }
-    if (metric == QA_METRIC_PCC)
-        return launch_cluster(greedy_par_kernel<true>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                              metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end, flags);
-    return launch_cluster(greedy_par_kernel<false>, pick_cluster(ntiles), (cudaStream_t)stream, table, (int)ntiles, numel,
-                          metric, threshold, ord, rng, assignment, counts, state, pw, have_init, pass_begin, pass_end, flags);
+    const int nr = pick_cluster(ntiles);
+    cudaStream_t cs = (cudaStream_t)stream;
+#define QA_LAUNCH_CHAIN(P, I)                                                                                                  \
+    launch_cluster(greedy_par_kernel<P, I>, nr, cs, table, (int)ntiles, numel, metric, threshold, ord, rng, assignment, counts, \
+                   state, pw, have_init, pass_begin, pass_end, flags)
+    if (metric == QA_METRIC_PCC) return have_init ? QA_LAUNCH_CHAIN(true, false) : QA_LAUNCH_CHAIN(true, true);
+    return have_init ? QA_LAUNCH_CHAIN(false, false) : QA_LAUNCH_CHAIN(false, true);
+#undef QA_LAUNCH_CHAIN
 }
 
 extern "C" int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, int metric, double threshold,
