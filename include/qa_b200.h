@@ -123,13 +123,16 @@ int qa_greedy_assign(const double* table, int64_t ntiles, double numel, int metr
                      int8_t* assignment, int64_t* counts, double* state, void* work,
                      qa_stream_t stream);
 
-/* Same contract as qa_greedy_assign / qa_numpy_permutation, computed by ONE 1024-thread block per
- * tensor instead of one thread: the sequentially-rounded float64 sums are carried by a prefix
+/* Same contract as qa_greedy_assign / qa_numpy_permutation, computed by ONE thread-block cluster
+ * per tensor (up to 16 CTAs of 256 threads exchanging scan totals through distributed shared
+ * memory) instead of one thread: the sequentially-rounded float64 sums are carried by a prefix
  * scan that reproduces every rounding, the accept/reject chain is resolved by speculation to its
  * sequential fixed point, and the NumPy permutation is generated and applied in parallel
  * (csrc/qa_greedy_par.cu).  metric: pcc or mae (atol keeps the sequential kernel).
- * state[6] = degraded-column bits (bit0 sum x, bit1 sum y of the INITIAL sums were finished with a
- * tree sum because they kept changing binade) + 65536 * speculation rounds.
+ * state[6] = flag bits (bit0 sum x, bit1 sum y of the INITIAL sums of a zero-mean tensor were taken
+ * as fixed-order tree sums; bit2 sum y ran on a fixed coarser grid during a pass that could carry
+ * it across a binade boundary) + 65536 * speculation rounds; state[7] = final metric value;
+ * state[11] = max |x - y| of the final assignment; the rest are cycle counters (profiles/).
  * work: at least qa_greedy_par_work_bytes(n) bytes. */
 int64_t qa_greedy_par_work_bytes(int64_t n);
 int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric,
