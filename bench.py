@@ -53,10 +53,13 @@ def config_dict(n_gpus: int) -> dict:
 # clocks sampler (NVML)
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._thr = None
+        self.nv = None
+        if not enabled:
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -265,13 +268,23 @@ def main() -> None:
     run_steps(W, INFLIGHT)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        run_steps(K, INFLIGHT)
-        e1.record()
-        barrier()
-    ms = reduce_max(e0.elapsed_time(e1))
+    # SM clocks / throttle reasons are sampled from here to the end of the end-to-end region (both timed regions); on rank 0
+    # only: NVML queries from every rank of a node serialise in the driver and steal host time from the launch threads
+    clk = ClockSampler(local, enabled=(rank == 0))
+    clk.__enter__()
+    barrier()
+    e0.record()
+    run_steps(K, INFLIGHT)
+    e1.record()
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    ms = reduce_max(ms_local)
+    per_rank_ms = [ms_local / K]
+    if world > 1:                                   # every rank's own device time per step (the value uses the max)
+        t = torch.tensor([ms_local / K], dtype=torch.float64, device=dev)
+        buf = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(buf, t)
+        per_rank_ms = [float(b.item()) for b in buf]
     value = world * nbytes * K / (ms * 1e-3) / 1e9
     # latency of one step with nothing else in flight
     run_steps(2, 1)
@@ -308,6 +321,7 @@ def main() -> None:
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0)
     e2e_value = world * nbytes * K / e2e_s / 1e9
+    clk.__exit__()
     # the ceiling of that number: a plain pinned-host -> device copy of the same bytes (the PCIe link of this GPU)
     big = max(range(len(host)), key=lambda i: host[i].numel())
     dst = torch.empty_like(host[big], device=dev)
@@ -384,6 +398,7 @@ def main() -> None:
                         "api": "GreedyBatch.enqueue_from_host(pinned bf16 host tensors) / finish() -> assignment maps + pcc/mae/atol on host, two batches alternating"},
                 "gpu_launches": batch.launches_per_step * K,
                 "step_latency_ms": ms_single,
+                "per_rank_ms_per_step": per_rank_ms,
                 "roofline": roofline, "roofline_by_kernel": kernels,
                 "pct_of_8TBs": 100.0 * value / world / 8000.0,
                 "result_check": {"counts_q_a_proj": results[0]["counts"], "pcc_q_a_proj": results[0]["metrics"]["pcc"],
