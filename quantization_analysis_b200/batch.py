@@ -1,9 +1,22 @@
 """Multi-tensor batching of the quantize-and-score path (the per-tensor loop of wq:655-709).
 
 ``GreedyBatch`` owns every device buffer for a list of same-run tensors and enqueues, per
-tensor, the fused tile-stat pass, the greedy assignment and the whole-tensor sums on a small
-pool of CUDA streams, with no host synchronisation until ``collect()``.  Tensors are independent
-(the reference processes them one after another), so a rank's shard is just a sub-list.
+tensor, the stages of the path on a small pool of CUDA streams, with no host synchronisation
+until ``collect()`` / ``finish()``.  Tensors are independent (the reference processes them one
+after another), so a rank's shard is just a sub-list.
+
+Schedule of one tensor (every stage is a C-ABI call):
+
+    side stream   resolve permutations #1,#2 ........ resolve #3 .. apply #3 ..............\
+    side2 stream                       apply #2 ......\                                    \
+    stats stream  tile stats [rows A | B | C] . deltas \                                    \
+    main stream        init sums A ... B ........ C ... chain passes 0-1 ... chain passes 2+ ... (D2H)
+
+* the permutations depend on (seed, tile count) only: tensors of equal tile count share them;
+* the table of a large tensor is produced in row ranges, its sequential init sums run underneath;
+* tile-stat passes of all tensors are serialized largest first, cluster kernels get priority;
+* ``capture()`` / ``run_graph()`` replay the whole list as one CUDA graph;
+* ``enqueue_from_host()`` / ``finish()`` is the asynchronous end-to-end form (pinned host in, pinned host out).
 """
 from __future__ import annotations
 
