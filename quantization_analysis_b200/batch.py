@@ -1,4 +1,4 @@
-"""Multi-tensor batching of the quantize-and-score path (the per-tensor loop of wq:655-709).
+r"""Multi-tensor batching of the quantize-and-score path (the per-tensor loop of wq:655-709).
 
 ``GreedyBatch`` owns every device buffer for a list of same-run tensors and enqueues, per
 tensor, the stages of the path on a small pool of CUDA streams, with no host synchronisation
