@@ -68,6 +68,12 @@ const char* qa_last_error(void);
 int qa_quant_recon(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
                    uint32_t fmt_mask, void* const out[QA_NFMT], qa_stream_t stream);
 
+/* qa_quant_recon with the shared exponent along COLUMNS: groups are 16 consecutive rows of one column (rows beyond the
+ * end read as zero).  Replaces compression_algorithms/transpose.py:13-33 (quantize x.T, transpose back) without moving
+ * the data: for an n-d array pass rows = shape[0], cols = prod(shape[1:]).  The bf16 format (bit 0) is elementwise. */
+int qa_quant_recon_cols(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                        uint32_t fmt_mask, void* const out[QA_NFMT], qa_stream_t stream);
+
 /* mxfp4 (which = 0) / nvfp4 (which = 1) scalar proxies: the elementwise maps quantize_weight_values applies for these two
  * formats (quantization_formats.py:171-183; simulate_mxfp4_amax / simulate_nvfp4_amax :254-278 on a block of identical
  * values).  x: bf16 or float32 [n]; out: float32 [n]. */
@@ -103,6 +109,11 @@ int qa_tile_stats_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, i
  * scores[(metric * QA_NFMT + f) * ntiles + tile], float32, for all three metrics. */
 int qa_tile_scores_f32(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
                        uint32_t fmt_mask, float* scores, qa_stream_t stream);
+
+/* tile_metrics(ref_tiles, q_tiles, metric) for arbitrary operands (tile_utils.py:46-57): float32 [ntiles][32][32] stacks
+ * of reference and candidate tiles -> scores float32 [3][ntiles] (pcc, mae, atol), same float32 orders. */
+int qa_tile_scores_pair_f32(const float* ref_tiles, const float* q_tiles, int64_t ntiles, float* scores,
+                            qa_stream_t stream);
 
 /* numpy.random.Generator.permutation(n) / .integers(0, k, n) continued from *rng on device
  * (mixed_tile_greedy.py:225,231; mixed_tile_random.py:116,133).  out_perm: int32[n];
@@ -260,6 +271,24 @@ int qa_assignment_sums_batch(const double* table, int64_t ntiles, const int8_t* 
  * work: qa_pair_sums_work_bytes() bytes. */
 int64_t qa_pair_sums_work_bytes(void);
 int qa_pair_sums(const float* a, const float* b, int64_t n, double* out, void* work, qa_stream_t stream);
+
+/* Whole-tensor NumPy-float32-faithful scores: compression_algorithms/metrics.py:6-27 (pearson_corr, mae, atol) as the
+ * reference evaluates them on flattened tensors at wq:684-687, scripts/sweep_mixed_tile_threshold.py:746-749 and
+ * mixed_tile_random.py:137-141 - np.mean = pairwise float32 sum, np.dot = OpenBLAS 0.3.30 SkylakeX sdot (64 FMA chains,
+ * its folds, the 32-element block and the double-accumulated tail), float32 sqrt / multiply / divide.
+ *
+ *  qa_pairwise_plan_words / qa_pairwise_plan_build - HOST helpers: the shape of np.add.reduce's pairwise tree over n
+ *      contiguous elements (it depends on n only).  plan_host receives qa_pairwise_plan_words(n) int32 words; word 2 is
+ *      the node count used by qa_tensor_scores_work_bytes.  The caller copies the plan to the device once per n.
+ *  qa_tensor_scores_f32 - x: n elements (bf16 patterns or float32); y: nbatch arrays of n elements, y_stride elements
+ *      apart (NULL = all zeros, the fp0 format); plan_dev: the plan on the device, plan_head_host: its first 4 words on
+ *      the host.  out float32 [nbatch][4] = {pcc, mae, atol, mean(y)}.  work: qa_tensor_scores_work_bytes(plan[2], nbatch). */
+int64_t qa_pairwise_plan_words(int64_t n);
+int qa_pairwise_plan_build(int64_t n, int32_t* plan_host);
+int64_t qa_tensor_scores_work_bytes(int64_t plan_nnodes, int nbatch);
+int qa_tensor_scores_f32(const void* x, int x_dtype, const void* y, int y_dtype, int64_t y_stride, int nbatch, int64_t n,
+                         const int32_t* plan_dev, const int32_t* plan_head_host, float* out, void* work,
+                         qa_stream_t stream);
 
 /* fp32 -> bf16 bit patterns plus a count of elements that are NOT bf16-exact (low 16 bits != 0).
  * Host helper for the numpy-in API.  inexact_count: uint64 on device (accumulated). */

@@ -250,27 +250,64 @@ def _fma_f32(a: np.ndarray, b: np.ndarray, c: np.ndarray) -> np.ndarray:
 
 
 def np_sdot_f32(x: np.ndarray, y: np.ndarray) -> np.ndarray:
-    """``np.dot`` of float32 vectors as OpenBLAS 0.3.30's SkylakeX ``sdot`` evaluates it.
+    """``np.dot`` of float32 vectors as OpenBLAS 0.3.30's SkylakeX ``sdot`` evaluates it (pinned against np.dot in
+    tests/test_oracle_golden.py for many n, same image).
 
-    64 FMA accumulators (4 vectors x 16 lanes); element i feeds accumulator
-    (i%64)//16, lane i%16, in increasing i.  Fold: lanes l and l+8 of each
-    accumulator, then ((A0+A1)+A2)+A3, then lanes l and l+4, then
-    (v0+v1)+(v2+v3).  Vectorised over leading axes; n must be a multiple of 64
-    (all 32x32 tiles are).  Pinned against np.dot in tests (same image).
+    n1 = n & -32 elements go through the vector kernel: blocks of 64 feed 64 FMA accumulators (4 vectors x 16 lanes;
+    element i -> accumulator (i%64)//16, lane i%16, increasing i); lanes l and l+8 of each accumulator are added
+    (-> 4 x 8 lanes); a remaining block of 32 is one more FMA into those 4 x 8 lanes; then ((A0+A1)+A2)+A3, lanes l and
+    l+4, (v0+v1)+(v2+v3).  The last n%32 elements are summed separately: float32 products accumulated in a DOUBLE that
+    starts at 0; the result is float32(double_tail + kernel).  Vectorised over leading axes.
     """
     n = x.shape[-1]
-    if n % 64:
-        raise ValueError("np_sdot_f32 restatement covers n % 64 == 0 only")
     lead = x.shape[:-1]
-    xs = x.reshape(lead + (n // 64, 4, 16))
-    ys = y.reshape(lead + (n // 64, 4, 16))
+    n1 = n & -32
+    n64 = n1 & ~63
     acc = np.zeros(lead + (4, 16), dtype=np.float32)
-    for it in range(n // 64):
-        acc = _fma_f32(xs[..., it, :, :], ys[..., it, :, :], acc)
+    if n64:
+        xs = x[..., :n64].reshape(lead + (n64 // 64, 4, 16))
+        ys = y[..., :n64].reshape(lead + (n64 // 64, 4, 16))
+        for it in range(n64 // 64):
+            acc = _fma_f32(xs[..., it, :, :], ys[..., it, :, :], acc)
     h = acc[..., :, :8] + acc[..., :, 8:]
+    if n1 - n64 == 32:
+        h = _fma_f32(x[..., n64:n1].reshape(lead + (4, 8)), y[..., n64:n1].reshape(lead + (4, 8)), h)
     s = ((h[..., 0, :] + h[..., 1, :]) + h[..., 2, :]) + h[..., 3, :]
     q = s[..., :4] + s[..., 4:]
-    return (q[..., 0] + q[..., 1]) + (q[..., 2] + q[..., 3])
+    kern = ((q[..., 0] + q[..., 1]) + (q[..., 2] + q[..., 3])).astype(np.float32)
+    if n1 == n:
+        return kern
+    tail = np.zeros(lead, dtype=np.float64)
+    for i in range(n1, n):
+        tail = tail + (y[..., i] * x[..., i]).astype(np.float32).astype(np.float64)
+    return (tail + kern.astype(np.float64)).astype(np.float32)
+
+
+def pearson_f32_restated(a: np.ndarray, b: np.ndarray) -> float:
+    """metrics.py:6-16 on whole (flattened) tensors with the NumPy / OpenBLAS summation orders restated explicitly:
+    the value the reference prints, reproduced without calling np.mean / np.dot (what the CUDA scorer is checked against)."""
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    b = np.ascontiguousarray(b, dtype=np.float32).reshape(-1)
+    if a.size == 0:
+        return 1.0
+    n = np.float32(a.size)
+    am = a - np.float32(np_pairwise_sum(a) / n)
+    bm = b - np.float32(np_pairwise_sum(b) / n)
+    na = np.sqrt(np.float32(np_sdot_f32(am, am)))
+    nb = np.sqrt(np.float32(np_sdot_f32(bm, bm)))
+    denom = float(np.float32(na * nb))
+    if denom == 0.0:
+        return 1.0 if np.max(np.abs(a - b)) == 0.0 else 0.0
+    return float(np.float32(np_sdot_f32(am, bm)) / np.float32(denom))
+
+
+def wq_scores_restated(x: np.ndarray, y: np.ndarray) -> dict:
+    """wq:684-687 (mae, atol, pcc of a result against the input), restated orders."""
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1)
+    y = np.ascontiguousarray(y, dtype=np.float32).reshape(-1)
+    d = np.abs(x - y)
+    mae = float(np.float32(np_pairwise_sum(d) / np.float32(d.size))) if d.size else float("nan")
+    return {"pcc": pearson_f32_restated(x, y), "mae": mae, "atol": float(d.max()) if d.size else float("nan")}
 
 
 # --------------------------------------------------------------------------- #

@@ -20,10 +20,11 @@ NFMT, NSTAT = 4, 22
 STATS_FAST, STATS_STRICT, STATS_FAST_APPROX_ABS = 0, 1, 2
 
 EXPORTS = [
-    "qa_version", "qa_last_error", "qa_quant_recon", "qa_tile_stats", "qa_tile_scores_f32",
+    "qa_version", "qa_last_error", "qa_quant_recon", "qa_quant_recon_cols", "qa_tile_stats", "qa_tile_scores_f32", "qa_tile_scores_pair_f32",
     "qa_numpy_permutation", "qa_numpy_integers", "qa_greedy_work_bytes", "qa_greedy_assign",
     "qa_threshold_assign", "qa_random_samples", "qa_apply_assignment", "qa_assignment_sums", "qa_assignment_sums_batch",
     "qa_f32_to_bf16_checked", "qa_scalar_proxy", "qa_fp8_block_dequant", "qa_greedy_par_work_bytes", "qa_greedy_assign_par", "qa_numpy_permutation_par", "qa_collective_bench", "qa_debug_times", "qa_greedy_cluster_cap", "qa_greedy_prefetch", "qa_greedy_assign_par_pre", "qa_greedy_assign_passes", "qa_greedy_init", "qa_greedy_init_sums", "qa_greedy_init_sums_range", "qa_greedy_init_deltas", "qa_tile_stats_rows", "qa_greedy_init_bytes", "qa_perm_resolve", "qa_perm_resolve_chain", "qa_perm_apply", "qa_perm_apply_work_bytes", "qa_pair_sums", "qa_pair_sums_work_bytes",
+    "qa_pairwise_plan_words", "qa_pairwise_plan_build", "qa_tensor_scores_work_bytes", "qa_tensor_scores_f32",
 ]
 
 
@@ -63,8 +64,10 @@ def lib():
     L.qa_version.restype = i32
     L.qa_last_error.restype = C.c_char_p
     L.qa_quant_recon.argtypes = [vp, i32, i64, i64, i64, u32, C.POINTER(vp), vp]
+    L.qa_quant_recon_cols.argtypes = L.qa_quant_recon.argtypes
     L.qa_tile_stats.argtypes = [vp, i32, i64, i64, i64, i64, u32, i32, vp, vp]
     L.qa_tile_scores_f32.argtypes = [vp, i32, i64, i64, i64, u32, vp, vp]
+    L.qa_tile_scores_pair_f32.argtypes = [vp, vp, i64, vp, vp]
     L.qa_numpy_permutation.argtypes = [vp, i64, vp, vp, vp]
     L.qa_numpy_integers.argtypes = [vp, i32, i64, vp, vp]
     L.qa_greedy_work_bytes.argtypes = [i64]
@@ -103,10 +106,16 @@ def lib():
     L.qa_f32_to_bf16_checked.argtypes = [vp, i64, vp, vp, vp]
     L.qa_scalar_proxy.argtypes = [vp, i32, i64, i32, vp, vp]
     L.qa_fp8_block_dequant.argtypes = [vp, vp, i64, i64, i64, i64, vp, vp, vp, vp]
+    L.qa_pairwise_plan_words.argtypes = [i64]
+    L.qa_pairwise_plan_words.restype = i64
+    L.qa_pairwise_plan_build.argtypes = [i64, vp]
+    L.qa_tensor_scores_work_bytes.argtypes = [i64, i32]
+    L.qa_tensor_scores_work_bytes.restype = i64
+    L.qa_tensor_scores_f32.argtypes = [vp, i32, vp, i32, i64, i32, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("qa_last_error", "qa_greedy_work_bytes", "qa_greedy_par_work_bytes", "qa_greedy_init_bytes", "qa_perm_apply_work_bytes", "qa_version",
-                        "qa_pair_sums_work_bytes"):
+                        "qa_pair_sums_work_bytes", "qa_pairwise_plan_words", "qa_tensor_scores_work_bytes"):
             fn.restype = i32
     _lib = L
     return L

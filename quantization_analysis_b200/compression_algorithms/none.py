@@ -43,6 +43,8 @@ class NoneCompression(CompressionAlgorithm):
     name = "none"
 
     def run(self, xf, formats, quantizer=None, cache=None):
+        if quantizer is not None and getattr(quantizer, "backend", "emulation") != "emulation":
+            raise RuntimeError("the ttnn backend is not available in this build (emulation only)")
         cached = {}
         if cache is not None:
             for fmt in formats:

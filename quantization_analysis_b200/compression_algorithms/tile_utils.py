@@ -78,10 +78,8 @@ def reconstruct_from_tiles(tiles, shape_info, pad_info, tile_hw: int = 32):
 
 
 def tile_metrics(ref_tiles, q_tiles, metric: str) -> np.ndarray:
-    """Per-tile float32 score of [N,32,32] tile stacks (tile_utils.py:46-57), evaluated on the GPU
-    with NumPy's float32 summation orders.  q_tiles must be the quantization of ref_tiles in one
-    of the mixed-tile formats (that is the only way the reference calls it); the format is
-    identified by comparing reconstructions bit-for-bit."""
+    """Per-tile float32 score of two [N,32,32] tile stacks (tile_utils.py:46-57) on the GPU, with NumPy's float32
+    summation orders (qa_tile_scores_pair_f32): any pair of operands, like the reference."""
     if metric not in _METRICS:
         raise ValueError(f"Unsupported metric: {metric}")
     ref = np.ascontiguousarray(np.asarray(ref_tiles, dtype=np.float32))
@@ -89,12 +87,37 @@ def tile_metrics(ref_tiles, q_tiles, metric: str) -> np.ndarray:
     n = ref.shape[0]
     if n == 0:
         return np.zeros((0,), dtype=np.float32)
-    stacked = ref.reshape(n * 32, 32)
-    p = engine.prepare_tiles(stacked)
-    recon = engine.quant_recon(p, MIXED_TILE_FORMATS)
-    qd = torch.from_numpy(q.reshape(-1)).to(p.data.device)
-    for fmt in MIXED_TILE_FORMATS:
-        if torch.equal(recon[fmt].to(torch.float32), qd):
-            scores = engine.tile_scores(p, [fmt])
-            return scores[_METRICS.index(metric), engine.FMT_INDEX[fmt]].cpu().numpy()
-    raise ValueError("tile_metrics: q_tiles is not a mixed-tile-format quantization of ref_tiles")
+    if ref.shape != q.shape or ref.size != n * 1024:
+        raise ValueError("tile_metrics expects two [N, 32, 32] stacks of equal shape")
+    return engine.tile_scores_pair(ref, q)[_METRICS.index(metric)]
+
+
+def global_metric(xf, tiles, shape_info, pad_info, metric: str) -> float:
+    """metric_value of the un-tiled reconstruction against xf (tile_utils.py:135-137)."""
+    from .metrics import metric_value
+    return metric_value(xf, reconstruct_from_tiles(tiles, shape_info, pad_info), metric)
+
+
+def kmeans_1d(values, k: int, max_iters: int = 25, seed: int = 0):
+    """1-D Lloyd iterations from quantile seeds (tile_utils.py:60-88; an unused helper of the reference, host-side
+    bookkeeping like there).  -> (labels int32 [n], centroids float32 [k])."""
+    v = np.asarray(values, dtype=np.float32).reshape(-1)
+    if v.size == 0:
+        return np.zeros((0,), dtype=np.int32), np.zeros((0,), dtype=np.float32)
+    k = max(1, min(k, v.size))
+    if k == 1:
+        return np.zeros((v.size,), dtype=np.int32), np.array([float(np.mean(v))], dtype=np.float32)
+    cent = np.quantile(v, np.linspace(0.0, 1.0, k, dtype=np.float32))
+    rng = np.random.default_rng(seed)
+    labels = np.zeros(v.size, dtype=np.int64)
+    for _ in range(max_iters):
+        labels = np.argmin(np.abs(v[:, None] - cent[None, :]), axis=1)
+        nxt = cent.copy()
+        for c in range(k):
+            members = v[labels == c]
+            nxt[c] = float(np.mean(members)) if members.size else float(v[rng.integers(0, v.size)])
+        done = np.allclose(nxt, cent, rtol=0.0, atol=1e-6)
+        cent = nxt
+        if done:
+            break
+    return labels.astype(np.int32), cent.astype(np.float32)

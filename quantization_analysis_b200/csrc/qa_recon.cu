@@ -258,6 +258,45 @@ __global__ void __launch_bounds__(256) f32_to_bf16_checked_kernel(const float* _
     if ((threadIdx.x & 31) == 0 && bad) atomicAdd(inexact, (unsigned long long)bad);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column groups (the `transpose` algorithm, compression_algorithms/transpose.py:13-33): the reference quantizes x.T and
+// transposes back, i.e. the shared exponent runs over 16 consecutive ROWS of one column (axis 0 of the original array,
+// all later axes flattened into `cols`).  A thread owns one column of one 16-row group: 16 loads that are coalesced
+// across the warp (consecutive columns), register maximum, 16 coalesced stores per format - no data ever moves through
+// a transposed copy.  Rows beyond `rows` read as +0 like the reference's zero padding.
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(256) recon_cols_kernel(const void* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                                         uint32_t fmt_mask, OutPtrs out) {
+    const int64_t ngr = cdiv(rows, GROUP);
+    const int64_t total = ngr * cols;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = it / cols, c = it - g * cols;
+        uint32_t u[GROUP];
+#pragma unroll
+        for (int i = 0; i < GROUP; ++i) {
+            const int64_t r = g * GROUP + i;
+            uint32_t v = 0;
+            if (r < rows) {
+                if (DT == QA_DT_BF16) v = (uint32_t)reinterpret_cast<const uint16_t*>(x)[r * ld + c] << 16;
+                else v = reinterpret_cast<const uint32_t*>(x)[r * ld + c];
+            }
+            u[i] = v;
+        }
+        const uint32_t E = group_max_exp(u);
+#pragma unroll
+        for (int f = 0; f < QA_NFMT; ++f) {
+            if (!((fmt_mask >> f) & 1u)) continue;
+            uint16_t* o = reinterpret_cast<uint16_t*>(out.p[f]);
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) {
+                const int64_t r = g * GROUP + i;
+                if (r < rows) o[r * cols + c] = (uint16_t)(recon_bits(f, u[i], E) >> 16);
+            }
+        }
+    }
+}
+
 static inline bool vec_ok(const void* x, int dt, int64_t cols, int64_t ld, void* const* outs, int nout) {
     if (cols % GROUP || ld % GROUP) return false;
     if (reinterpret_cast<uintptr_t>(x) % 32) return false;
@@ -303,6 +342,24 @@ extern "C" int qa_quant_recon(const void* x, int x_dtype, int64_t rows, int64_t 
         else recon_kernel<QA_DT_F32, false><<<grid, 256, 0, s>>>(x, rows, cols, ld, gpr, fmt_mask, o);
     }
     return check_launch("qa_quant_recon");
+}
+
+extern "C" int qa_quant_recon_cols(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,
+                                   uint32_t fmt_mask, void* const out[QA_NFMT], qa_stream_t stream) {
+    if (rows < 0 || cols < 0 || ld < cols) { set_error("qa_quant_recon_cols: bad shape"); return 1; }
+    if (x_dtype != QA_DT_BF16 && x_dtype != QA_DT_F32) { set_error("qa_quant_recon_cols: bad dtype"); return 1; }
+    fmt_mask &= 0xFu;
+    if (rows == 0 || cols == 0 || fmt_mask == 0) return 0;
+    OutPtrs o;
+    for (int f = 0; f < QA_NFMT; ++f) {
+        o.p[f] = (fmt_mask >> f) & 1u ? out[f] : nullptr;
+        if (((fmt_mask >> f) & 1u) && !out[f]) { set_error("qa_quant_recon_cols: null output for format %d", f); return 1; }
+    }
+    const int grid = grid_for(cdiv(rows, GROUP) * cols, 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (x_dtype == QA_DT_BF16) recon_cols_kernel<QA_DT_BF16><<<grid, 256, 0, s>>>(x, rows, cols, ld, fmt_mask, o);
+    else recon_cols_kernel<QA_DT_F32><<<grid, 256, 0, s>>>(x, rows, cols, ld, fmt_mask, o);
+    return check_launch("qa_quant_recon_cols");
 }
 
 extern "C" int qa_apply_assignment(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld,

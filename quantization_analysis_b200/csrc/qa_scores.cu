@@ -132,7 +132,9 @@ __global__ void __launch_bounds__(SC_WARPS * 32) tile_scores_kernel(
         }
         __syncwarp();
         const float mean_b = __fdiv_rn(pairwise1024([&](int r, int c) { return ys[r * SCP + c]; }, lane), 1024.f);
-        float ebb = 0.f, obb = 0.f, eab = 0.f, oab = 0.f, mx = 0.f;
+        float ebb = 0.f, obb = 0.f, eab = 0.f, oab = 0.f;
+        uint32_t mxb = 0u;      // max |x - y| as a bit pattern: non-negative floats order like unsigned ints, and a NaN
+                                // (np.max propagates it, tile_utils.py:55-56) orders above +inf
 #pragma unroll
         for (int r = 0; r < TILE; r += 2) {
             const float b0 = __fsub_rn(ys[r * SCP + lane], mean_b);
@@ -141,13 +143,14 @@ __global__ void __launch_bounds__(SC_WARPS * 32) tile_scores_kernel(
             obb = __fmaf_rn(b1, b1, obb);
             eab = __fmaf_rn(am[r], b0, eab);
             oab = __fmaf_rn(am[r + 1], b1, oab);
-            mx = fmaxf(mx, fabsf(__fsub_rn(xs[r * SCP + lane], ys[r * SCP + lane])));
-            mx = fmaxf(mx, fabsf(__fsub_rn(xs[(r + 1) * SCP + lane], ys[(r + 1) * SCP + lane])));
+            mxb = max(mxb, __float_as_uint(fabsf(__fsub_rn(xs[r * SCP + lane], ys[r * SCP + lane]))));
+            mxb = max(mxb, __float_as_uint(fabsf(__fsub_rn(xs[(r + 1) * SCP + lane], ys[(r + 1) * SCP + lane]))));
         }
         const float nb = __fsqrt_rn(sdot_fold(ebb, obb, lane));
         const float dab = sdot_fold(eab, oab, lane);
 #pragma unroll
-        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        for (int o = 16; o; o >>= 1) mxb = max(mxb, __shfl_xor_sync(0xFFFFFFFFu, mxb, o));
+        const float mx = __uint_as_float(mxb);
         const float denom = __fmul_rn(na, nb);
         float pcc;
         if (denom == 0.f) pcc = (mx == 0.f) ? 1.f : 0.f;      // metrics.py:14-15
@@ -159,6 +162,54 @@ __global__ void __launch_bounds__(SC_WARPS * 32) tile_scores_kernel(
             scores[(QA_METRIC_MAE * QA_NFMT + f) * ntiles + t] = mae;
             scores[(QA_METRIC_ATOL * QA_NFMT + f) * ntiles + t] = mx;
         }
+    }
+}
+
+// tile_metrics(ref_tiles, q_tiles, metric) for ARBITRARY tile stacks (tile_utils.py:46-57): both operands are given,
+// float32 [ntiles][32][32]; same summation orders as above.  scores: float32 [3][ntiles] (pcc, mae, atol).
+__global__ void __launch_bounds__(SC_WARPS * 32) tile_scores_pair_kernel(const float* __restrict__ ref, const float* __restrict__ q,
+                                                                         int64_t ntiles, float* __restrict__ scores) {
+    __shared__ float xs_all[SC_WARPS][TILE * SCP];
+    __shared__ float ys_all[SC_WARPS][TILE * SCP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * SC_WARPS + warp;
+    if (t >= ntiles) return;
+    float* xs = xs_all[warp];
+    float* ys = ys_all[warp];
+    for (int r = 0; r < TILE; ++r) {
+        xs[r * SCP + lane] = ref[t * 1024 + r * TILE + lane];
+        ys[r * SCP + lane] = q[t * 1024 + r * TILE + lane];
+    }
+    __syncwarp();
+    const float mean_a = __fdiv_rn(pairwise1024([&](int r, int c) { return xs[r * SCP + c]; }, lane), 1024.f);
+    const float mean_b = __fdiv_rn(pairwise1024([&](int r, int c) { return ys[r * SCP + c]; }, lane), 1024.f);
+    float eaa = 0.f, oaa = 0.f, ebb = 0.f, obb = 0.f, eab = 0.f, oab = 0.f;
+    uint32_t mxb = 0u;
+#pragma unroll
+    for (int r = 0; r < TILE; r += 2) {
+        const float a0 = __fsub_rn(xs[r * SCP + lane], mean_a), a1 = __fsub_rn(xs[(r + 1) * SCP + lane], mean_a);
+        const float b0 = __fsub_rn(ys[r * SCP + lane], mean_b), b1 = __fsub_rn(ys[(r + 1) * SCP + lane], mean_b);
+        eaa = __fmaf_rn(a0, a0, eaa); oaa = __fmaf_rn(a1, a1, oaa);
+        ebb = __fmaf_rn(b0, b0, ebb); obb = __fmaf_rn(b1, b1, obb);
+        eab = __fmaf_rn(a0, b0, eab); oab = __fmaf_rn(a1, b1, oab);
+        mxb = max(mxb, __float_as_uint(fabsf(__fsub_rn(xs[r * SCP + lane], ys[r * SCP + lane]))));
+        mxb = max(mxb, __float_as_uint(fabsf(__fsub_rn(xs[(r + 1) * SCP + lane], ys[(r + 1) * SCP + lane]))));
+    }
+    const float na = __fsqrt_rn(sdot_fold(eaa, oaa, lane)), nb = __fsqrt_rn(sdot_fold(ebb, obb, lane));
+    const float dab = sdot_fold(eab, oab, lane);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mxb = max(mxb, __shfl_xor_sync(0xFFFFFFFFu, mxb, o));
+    const float mx = __uint_as_float(mxb);
+    const float denom = __fmul_rn(na, nb);
+    float pcc;
+    if (denom == 0.f) pcc = (mx == 0.f) ? 1.f : 0.f;
+    else pcc = __fdiv_rn(dab, denom);
+    const float mae = __fdiv_rn(
+        pairwise1024([&](int r, int c) { return fabsf(__fsub_rn(xs[r * SCP + c], ys[r * SCP + c])); }, lane), 1024.f);
+    if (lane == 0) {
+        scores[QA_METRIC_PCC * ntiles + t] = pcc;
+        scores[QA_METRIC_MAE * ntiles + t] = mae;
+        scores[QA_METRIC_ATOL * ntiles + t] = mx;
     }
 }
 
@@ -179,4 +230,11 @@ extern "C" int qa_tile_scores_f32(const void* x, int x_dtype, int64_t rows, int6
         tile_scores_kernel<QA_DT_F32><<<(unsigned)grid, SC_WARPS * 32, 0, s>>>(x, rows, cols, ld, tiles_w, ntiles, fmt_mask & 0xFu, scores);
     else { set_error("qa_tile_scores_f32: bad dtype"); return 1; }
     return check_launch("qa_tile_scores_f32");
+}
+
+extern "C" int qa_tile_scores_pair_f32(const float* ref_tiles, const float* q_tiles, int64_t ntiles, float* scores, qa_stream_t stream) {
+    if (ntiles < 0 || !scores || (ntiles && (!ref_tiles || !q_tiles))) { set_error("qa_tile_scores_pair_f32: bad args"); return 1; }
+    if (ntiles == 0) return 0;
+    tile_scores_pair_kernel<<<(unsigned)cdiv(ntiles, SC_WARPS), SC_WARPS * 32, 0, (cudaStream_t)stream>>>(ref_tiles, q_tiles, ntiles, scores);
+    return check_launch("qa_tile_scores_pair_f32");
 }

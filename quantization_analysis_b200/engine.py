@@ -141,6 +141,24 @@ def quant_recon(p: Prepared, formats) -> dict[str, torch.Tensor]:
     return outs
 
 
+def quant_recon_cols(x, formats) -> tuple[dict[str, torch.Tensor], tuple]:
+    """bf16 reconstructions with the shared exponent along axis 0 (16 consecutive rows of a column; transpose.py:13-33:
+    quantize x.T, transpose back - computed in place by qa_quant_recon_cols, no transposed copy).  x: >= 2-D."""
+    shape = tuple(x.shape)
+    t, code = to_device(x)
+    rows, cols = int(shape[0]), int(np.prod(shape[1:]))
+    formats = [f for f in formats if f in FMT_INDEX]
+    outs: dict[str, torch.Tensor] = {}
+    arr = (C.c_void_p * NFMT)()
+    for f in formats:
+        o = torch.empty(rows * cols, dtype=torch.bfloat16, device=t.device)
+        outs[f] = o
+        arr[FMT_INDEX[f]] = o.data_ptr()
+    if rows * cols and formats:
+        check(_lib.lib().qa_quant_recon_cols(_ptr(t), code, rows, cols, cols, fmt_mask(formats), arr, _stream()), "qa_quant_recon_cols")
+    return outs, shape
+
+
 def tile_stats(p: Prepared, formats=MIXED_FORMATS, strict: bool | None = None, exact_abs: bool = True) -> torch.Tensor:
     """float64 [NSTAT, ntiles] tile-stat table.  strict=None picks fast for bf16 input.
     exact_abs=False lets the fast kernel keep sum|x-y| in fp32 group partials (~1e-9 relative):
@@ -185,6 +203,17 @@ def tile_scores(p: Prepared, formats=MIXED_FORMATS) -> torch.Tensor:
     check(_lib.lib().qa_tile_scores_f32(_ptr(p.data), p.dtype_code, p.rows, p.cols, p.cols, fmt_mask(formats), _ptr(s), _stream()),
           "qa_tile_scores_f32")
     return s
+
+
+def tile_scores_pair(ref_tiles: np.ndarray, q_tiles: np.ndarray) -> np.ndarray:
+    """float32 [3, N] NumPy-faithful (pcc, mae, atol) of two arbitrary [N,32,32] float32 tile stacks."""
+    dev = _require_cuda()
+    r = torch.from_numpy(np.ascontiguousarray(ref_tiles, dtype=np.float32).reshape(-1)).to(dev)
+    q = torch.from_numpy(np.ascontiguousarray(q_tiles, dtype=np.float32).reshape(-1)).to(dev)
+    n = r.numel() // 1024
+    s = torch.empty((3, n), dtype=torch.float32, device=dev)
+    check(_lib.lib().qa_tile_scores_pair_f32(_ptr(r), _ptr(q), n, _ptr(s), _stream()), "qa_tile_scores_pair_f32")
+    return s.cpu().numpy()
 
 
 def make_rng(seed: int, device=None) -> torch.Tensor:
@@ -453,3 +482,59 @@ def result_to_numpy(p: Prepared, y_bf16: torch.Tensor) -> np.ndarray:
     if p.kind == "vector" and y.numel() != p.numel:
         y = y[: p.numel]
     return y.to(torch.float32).cpu().numpy().reshape(p.shape)
+
+
+# --------------------------------------------------------------------------------------------
+# whole-tensor NumPy-float32-faithful scores (metrics.py:6-27 as wq:684-687 evaluates them)
+# --------------------------------------------------------------------------------------------
+_PLANS: dict = {}
+
+
+def pairwise_plan_host(n: int) -> np.ndarray:
+    """Shape of np.add.reduce's pairwise-summation tree over n contiguous elements (qa_pairwise_plan_build; host only)."""
+    L = _lib.lib()
+    words = L.qa_pairwise_plan_words(int(n))
+    plan = np.zeros(max(words, 4), dtype=np.int32)
+    check(L.qa_pairwise_plan_build(int(n), plan.ctypes.data), "qa_pairwise_plan_build")
+    return plan
+
+
+def _plan(n: int, dev: torch.device):
+    key = (int(n), dev.index)
+    if key not in _PLANS:
+        if len(_PLANS) > 32:
+            _PLANS.clear()
+        host = pairwise_plan_host(n)
+        _PLANS[key] = (host, torch.from_numpy(host).to(dev))
+    return _PLANS[key]
+
+
+def tensor_scores_f32(x: torch.Tensor, y: torch.Tensor | None, n: int | None = None) -> np.ndarray:
+    """float32 {pcc, mae, atol, mean(y)} of `y` against `x`, bit-faithful to the reference's NumPy evaluation on the
+    flattened tensors.  x: device tensor (bf16 / float32), its first n elements are scored; y: None (all zeros = fp0), a
+    tensor of >= n elements, or a [nbatch, m >= n] tensor of candidates scored in one call.  -> float32 [nbatch, 4]."""
+    dev = x.device
+    L = _lib.lib()
+    xf = x.reshape(-1)
+    n = int(xf.numel() if n is None else n)
+    if n <= 0:
+        raise ValueError("tensor_scores_f32: empty input")
+    code = lambda t: QA_DT_BF16 if t.dtype == torch.bfloat16 else QA_DT_F32      # noqa: E731
+    if xf.dtype not in (torch.bfloat16, torch.float32):
+        xf = xf.float()
+    if y is None:
+        nb, stride, yp, ydt = 1, 0, None, QA_DT_F32
+    else:
+        if y.dtype not in (torch.bfloat16, torch.float32):
+            y = y.float()
+        y2 = y.reshape(1, -1) if y.dim() <= 1 or y.numel() == xf.numel() else y.reshape(y.shape[0], -1)
+        y2 = y2.contiguous()
+        nb, stride, yp, ydt = y2.shape[0], y2.shape[1], y2, code(y2)
+        if stride < n:
+            raise ValueError("tensor_scores_f32: y is shorter than x")
+    host, plan = _plan(n, dev)
+    out = torch.empty((nb, 4), dtype=torch.float32, device=dev)
+    work = torch.empty(L.qa_tensor_scores_work_bytes(int(host[2]), nb), dtype=torch.uint8, device=dev)
+    check(L.qa_tensor_scores_f32(_ptr(xf), code(xf), _ptr(yp), ydt, stride, nb, n, _ptr(plan), host.ctypes.data, _ptr(out), _ptr(work),
+                                 _stream()), "qa_tensor_scores_f32")
+    return out.cpu().numpy()

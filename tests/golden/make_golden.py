@@ -238,6 +238,34 @@ def make_fp8_dequant() -> None:
     print("fp8_dequant.npz:", len(out), "arrays")
 
 
+def make_transpose() -> None:
+    """compression_algorithms/transpose.py (quantize x.T, transpose back) through the reference's plug-in, incl. ragged, 3-D,
+    1-D and genuinely-float32 inputs."""
+    quantizer = Quantizer(backend="emulation")
+    rng = np.random.default_rng(31)
+    cases = {k: v for k, v in algo_cases().items() if k in ("het_96x160", "het_70x45", "het_3d_2x40x64", "het_1d_1000")}
+    cases["rand_fp32_50x70"] = (rng.standard_normal((50, 70)) * 0.02).astype(np.float32)
+    cases["rand_fp32_4d"] = (rng.standard_normal((3, 5, 4, 9)) * 2).astype(np.float32)
+    out = {}
+
+    class _NoCache:
+        def load_array(self, *a):
+            return None
+
+        def save_array(self, *a):
+            return None
+
+    for name, x in cases.items():
+        out[f"{name}__in"] = bits(x)
+        out[f"{name}__shape"] = np.asarray(x.shape, dtype=np.int64)
+        res = create_algorithm("transpose", {}).run(xf=x, formats=FORMATS, quantizer=quantizer, cache=_NoCache())
+        for r in res:
+            assert r.y.shape == x.shape
+            out[f"{name}__{r.fmt.lower()}"] = bits(np.ascontiguousarray(r.y))
+    np.savez_compressed(HERE / "transpose_small.npz", **out)
+    print("transpose_small.npz:", len(out), "arrays")
+
+
 def make_cfg2() -> None:
     """The bench workload itself (configs[1], rank 0): the reference's mixed-tile-greedy pcc >= 0.999, seed 123, on the five
     layer-0 self_attn shapes with bench.py's synthetic bf16 tensors (seed 1000 + i).  Full size: 187 M elements, minutes."""
@@ -267,10 +295,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "scalar_proxies":
         make_scalar_proxies()
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "transpose":
+        make_transpose()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fp8_dequant":
         make_fp8_dequant()
         raise SystemExit(0)
     make_fp8_dequant()
+    make_transpose()
     make_scalar_proxies()
     make_kats()
     make_rng()
