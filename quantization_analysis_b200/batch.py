@@ -15,6 +15,8 @@ Schedule of one tensor (every stage is a C-ABI call):
 * the permutations depend on (seed, tile count) only: tensors of equal tile count share them;
 * the table of a large tensor is produced in row ranges, its sequential init sums run underneath;
 * tile-stat passes of all tensors are serialized largest first, cluster kernels get priority;
+* with ``perm_cache`` the permutations are drawn once per (device, seed, tile count, format count) for the whole process
+  (every layer of a model repeats the same shapes under one seed) and the per-step prefetch launches disappear;
 * ``capture()`` / ``run_graph()`` replay the whole list as one CUDA graph;
 * ``enqueue_from_host()`` / ``finish()`` is the asynchronous end-to-end form (pinned host in, pinned host out).
 """
@@ -28,14 +30,46 @@ from ._lib import METRIC_CODE, NFMT, NSTAT, STATS_FAST, STATS_FAST_APPROX_ABS, c
 
 MIXED = engine.MIXED_FORMATS
 
+# (device index, seed, ntiles, nfmt) -> {"pre_order": int32 [2, ntiles], "rngs": stream states after permutations #1..#3}.
+# NumPy's permutation of n items from a freshly seeded generator depends on nothing else, and the reference re-seeds per
+# tensor (mixed_tile_greedy.py:222-225): every tensor with the same tile count - the experts of a MoE layer, the same
+# projection in each of a model's 61 layers - visits its tiles in the same order.
+_PERM_CACHE: dict = {}
+
+
+def cached_permutations(device, seed: int, ntiles: int, nfmt: int):
+    """Visiting orders of greedy passes 2 and 3 and the generator states after permutations #1..#3, drawn once (synchronous,
+    outside any timed region or graph capture) and kept for the life of the process."""
+    key = (torch.device(device).index, int(seed), int(ntiles), int(nfmt))
+    hit = _PERM_CACHE.get(key)
+    if hit is not None:
+        return hit
+    L = _lib.lib()
+    dev = torch.device(device)
+    rng0 = engine.make_rng(seed, dev)
+    jarr = torch.empty((3, ntiles), dtype=torch.int32, device=dev)
+    pre_order = torch.empty((2, ntiles), dtype=torch.int32, device=dev)
+    rngs = torch.stack([rng0, rng0, rng0]).contiguous()
+    awork = torch.empty(L.qa_perm_apply_work_bytes(ntiles), dtype=torch.uint8, device=dev)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    check(L.qa_perm_resolve_chain(rng0.data_ptr(), ntiles, 2, 0b10, jarr.data_ptr(), rngs.data_ptr(), sp), "qa_perm_resolve_chain")
+    check(L.qa_perm_apply(jarr[1].data_ptr(), ntiles, None, pre_order[0].data_ptr(), awork.data_ptr(), sp), "qa_perm_apply")
+    if nfmt >= 3:
+        check(L.qa_perm_resolve(rngs[1].data_ptr(), ntiles, jarr[2].data_ptr(), rngs[2].data_ptr(), sp), "qa_perm_resolve")
+        check(L.qa_perm_apply(jarr[2].data_ptr(), ntiles, None, pre_order[1].data_ptr(), awork.data_ptr(), sp), "qa_perm_apply")
+    torch.cuda.current_stream(dev).synchronize()
+    _PERM_CACHE[key] = {"pre_order": pre_order, "rngs": rngs}
+    return _PERM_CACHE[key]
+
 
 class GreedyBatch:
     PIPELINE_MIN_TILES = 32768      # tensors at least this large produce their table in three row ranges (see _enqueue)
     PIPELINE_FIRST_TILES = 4096    # ... the first of at least this many tiles (or an eighth of the tensor)
 
     def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
-                 tile_formats=MIXED, n_streams: int | None = None, device=None):
+                 tile_formats=MIXED, n_streams: int | None = None, device=None, perm_cache: bool = False):
         self.device = device or engine._require_cuda()
+        self.perm_cache = bool(perm_cache)
         self.metric, self.threshold, self.seed = metric, float(threshold), int(seed)
         self.tile_formats = list(tile_formats)
         self.shapes = [tuple(int(v) for v in s) for s in shapes]
@@ -56,6 +90,7 @@ class GreedyBatch:
         self.stats_streams = [torch.cuda.Stream(device=self.device) for _ in range(1 if len(self.shapes) <= 16 else 4)]
         self._stats_rr = 0
         self.prefetch = metric != "atol" and len(self.tile_formats) >= 2
+        self.perm_cache = self.perm_cache and self.prefetch
         L = _lib.lib()
         self.slots = []
         rng0 = engine.make_rng(self.seed, self.device)
@@ -94,6 +129,10 @@ class GreedyBatch:
         for s_ in self.slots:                 # followers read the leader's permutations
             ld = self.slots[s_["leader"]]
             s_["pre_order"], s_["rngs"] = ld["pre_order"], ld["rngs"]
+        if self.perm_cache:                   # ... or everybody reads the process-wide cache
+            for s_ in self.slots:
+                hit = cached_permutations(self.device, self.seed, s_["ntiles"], len(self.tile_formats))
+                s_["pre_order"], s_["rngs"] = hit["pre_order"], hit["rngs"]
         self._rng0 = rng0
         self._graphs = {}
         self.trace = None            # set to {} to record per-tensor stage events during eager run() (see timeline())
@@ -110,7 +149,9 @@ class GreedyBatch:
             else:
                 lead = self.slots[s["leader"]] is s
                 n = 5 if len(self.tile_formats) >= 3 else 4
-                if lead:
+                if self.perm_cache and len(self.tile_formats) >= 3:
+                    n -= 1                       # resident permutations: the chain is one launch
+                if lead and not self.perm_cache:
                     n += (2 + 2 * 7) if len(self.tile_formats) >= 3 else (1 + 7)
             if metric != "atol" and s["ntiles"] >= self.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8:
                 n += 4
@@ -139,12 +180,19 @@ class GreedyBatch:
 
         mark("start")
         lead = self.slots[slot["leader"]] is slot
-        if pre and not lead:
+        cached = pre and self.perm_cache           # permutations already resident: nothing to draw, nothing to wait for
+        if cached:
+            side, side2 = side
+            side2.wait_stream(stream)
+            with torch.cuda.stream(side2):
+                slot["rng"].copy_(self._rng0, non_blocking=True)
+            lead = False
+        elif pre and not lead:
             side, side2 = side
             side2.wait_stream(stream)
             with torch.cuda.stream(side2):
                 slot["rng"].copy_(self._rng0, non_blocking=True)      # off the stats -> init -> chain path
-        if pre and lead:
+        if pre and lead and not cached:
             # the first permutations depend only on (seed, ntiles): draw them on side streams while the tile-stat pass
             # streams the tensor.  Resolves chain through the RNG state (#1 -> #2 -> #3, one cluster each); each apply
             # only needs its own swap targets and runs as grid kernels, #2's on a second side stream next to resolve #3.
@@ -179,7 +227,7 @@ class GreedyBatch:
                 check(L.qa_perm_apply(slot["jarr"][1].data_ptr(), n, None, slot["pre_order"][0].data_ptr(),
                                       slot["apply_work"][0].data_ptr(), sa), "qa_perm_apply")
                 slot["ev_a2"].record(side)
-        if pre and lead:
+        if pre and lead and not cached:
             mark("prefetch", side)
         mode = STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS
         iargs = (slot["table"].data_ptr(), slot["ntiles"], METRIC_CODE[self.metric], self._order, len(self.tile_formats),
@@ -244,14 +292,18 @@ class GreedyBatch:
                     # passes 0-1 only need permutation #2 (applied on side2 while #3 is still being drawn); the later
                     # passes wait for the speculative #3 (applied last on the leader's side stream)
                     stream.wait_stream(side2)                 # own seed copy (and, for a leader, apply #2)
-                    stream.wait_event(ld["ev_a2"])
-                    check(L.qa_greedy_assign_passes(*pargs, 0, 2, 0, sp), "qa_greedy_assign_passes")
-                    stream.wait_event(ld["ev_a3"])
-                    check(L.qa_greedy_assign_passes(*pargs, 2, nf, SKIP, sp), "qa_greedy_assign_passes")
+                    if cached:                                # both permutations are resident: one launch for all passes
+                        check(L.qa_greedy_assign_passes(*pargs, 0, nf, SKIP, sp), "qa_greedy_assign_passes")
+                    else:
+                        stream.wait_event(ld["ev_a2"])
+                        check(L.qa_greedy_assign_passes(*pargs, 0, 2, 0, sp), "qa_greedy_assign_passes")
+                        stream.wait_event(ld["ev_a3"])
+                        check(L.qa_greedy_assign_passes(*pargs, 2, nf, SKIP, sp), "qa_greedy_assign_passes")
                 else:
                     if pre:
                         stream.wait_stream(side2 if not lead else side)
-                        stream.wait_event(ld["ev_a2"])
+                        if not cached:
+                            stream.wait_event(ld["ev_a2"])
                     check(L.qa_greedy_assign_passes(*pargs, 0, nf, SKIP, sp), "qa_greedy_assign_passes")
             mark("chain")
             if self.metric == "atol":      # the cluster kernel leaves the final sums (and max) in `state`

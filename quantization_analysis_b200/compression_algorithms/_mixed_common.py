@@ -50,10 +50,21 @@ class DeviceResult:
     assignment: torch.Tensor | None        # int8 [ntiles] (device) for mixed results
     counts: dict
     tile_bytes: float
-    metrics: dict                          # exact pcc / mae / atol of the result, from the table
+    metrics_exact: dict                    # float64 recombination of pcc / mae / atol from the tile-stat table
     tile_formats: list[str]
     meta: dict = field(default_factory=dict)
     _y: torch.Tensor | None = None
+    _metrics: dict | None = None
+
+    @property
+    def metrics(self) -> dict:
+        """pcc / mae / atol of the result as the reference reports them (wq:684-687): float32, NumPy's summation orders
+        (qa_tensor_scores_f32 over x and the materialised reconstruction)."""
+        if self._metrics is None:
+            p = self.prepared
+            s = engine.tensor_scores_f32(p.data, self.y_device(), n=p.numel)[0]
+            self._metrics = {"pcc": float(s[0]), "mae": float(s[1]), "atol": float(s[2])}
+        return self._metrics
 
     def y_device(self) -> torch.Tensor:
         """bf16 reconstruction on the device (materialised on first use)."""

@@ -15,7 +15,7 @@ from .tile_utils import counts_from_array, counts_to_array, format_tag
 def _safe_tensor_key(tensor_name: str) -> str:
     """File-system-safe tensor key: sanitised name + sha1 prefix (hf_model_utils.py:121-126)."""
     digest = hashlib.sha1(tensor_name.encode("utf-8")).hexdigest()[:12]
-    safe = re.sub(r"[^A-Za-z0-9._-]+", "_", tensor_name).strip("._-") or "tensor"
+    safe = re.sub(r"[^A-Za-z0-9._-]+", "_", tensor_name).strip("_") or "tensor"
     return f"{safe}--{digest}"
 
 

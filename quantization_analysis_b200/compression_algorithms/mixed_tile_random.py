@@ -3,7 +3,10 @@
 All `iters` uniform assignments are drawn from the NumPy PCG64 stream on the device and scored
 from the tile-stat table in one launch (qa_random_samples); selection over the per-sample
 scalars follows the reference's rules (smallest bytes among passing samples, first wins ties;
-otherwise strictly best metric).  Sample metrics are float64 recombinations.
+otherwise strictly best metric).  The per-sample pcc / mae / atol are the reference's float32 whole-tensor values
+(mixed_tile_random.py:137-141): every sample's reconstruction is materialised by qa_apply_assignment and scored by
+qa_tensor_scores_f32 in batches, so the selection - ties and near-ties included - is the reference's.
+``params["sample_scoring"] = "exact"`` (extension) keeps the float64 table recombinations instead (no reconstruction).
 """
 from __future__ import annotations
 
@@ -26,6 +29,7 @@ class MixedTileRandomCompression(CompressionAlgorithm):
         self.iters = int(self.params.get("iters", 50))
         self.seed = int(self.params.get("seed", 0))
         self.formats = mc.parse_formats(self.params.get("formats"))
+        self.sample_scoring = str(self.params.get("sample_scoring", "reference"))
         if self.metric not in mc.VALID_METRICS:
             raise ValueError(f"Unsupported metric: {self.metric}")
         if self.iters < 1:
@@ -52,6 +56,8 @@ class MixedTileRandomCompression(CompressionAlgorithm):
         iters = max(1, self.iters)
         choices, metrics_dev, counts_dev = engine.random_samples(table, p.numel, fmt_list, iters, rng)
         met = metrics_dev.cpu().numpy()
+        if self.sample_scoring != "exact":
+            met = self._reference_scores(p, choices)
         cnt = counts_dev.cpu().numpy().astype(np.int64)
         bpe32 = np.asarray([MIXED_TILE_BYTES_PER_ELEM[f] for f in MIXED_TILE_FORMATS], dtype=np.float32)
         col = {"pcc": 0, "mae": 1, "atol": 2}[self.metric]
@@ -71,8 +77,29 @@ class MixedTileRandomCompression(CompressionAlgorithm):
         assignment = choices[best_id].contiguous()
         counts = {f: int(cnt[best_id, i]) for i, f in enumerate(MIXED_TILE_FORMATS)}
         metrics = {"pcc": float(met[best_id, 0]), "mae": float(met[best_id, 1]), "atol": float(met[best_id, 2])}
-        return mc.DeviceResult(self.name, p, assignment, counts, mc.total_bytes(counts), metrics, fmt_list,
-                               meta={"samples": samples, "best_id": best_id})
+        dr = mc.DeviceResult(self.name, p, assignment, counts, mc.total_bytes(counts), metrics, fmt_list,
+                             meta={"samples": samples, "best_id": best_id})
+        if self.sample_scoring != "exact":
+            dr._metrics = dict(metrics)            # already the reference's float32 values of the chosen sample
+        return dr
+
+    @staticmethod
+    def _reference_scores(p: engine.Prepared, choices) -> np.ndarray:
+        """float32 (pcc, mae, atol) of every sample, [iters, 3] as float64 values of the float32 results."""
+        import torch
+        iters = choices.shape[0]
+        per = p.rows * p.cols
+        chunk = max(1, min(iters, (1 << 29) // max(per, 1)))          # <= 1 GiB of bf16 reconstructions at a time
+        out = np.zeros((iters, 3), dtype=np.float64)
+        ys = torch.empty((chunk, per), dtype=torch.bfloat16, device=p.data.device)
+        L = engine._lib.lib()
+        for s0 in range(0, iters, chunk):
+            k = min(chunk, iters - s0)
+            for j in range(k):
+                engine.check(L.qa_apply_assignment(p.data.data_ptr(), p.dtype_code, p.rows, p.cols, p.cols,
+                                                   choices[s0 + j].data_ptr(), ys[j].data_ptr(), engine._stream()), "qa_apply_assignment")
+            out[s0:s0 + k] = engine.tensor_scores_f32(p.data, ys[:k], n=p.numel)[:, :3].astype(np.float64)
+        return out
 
     def _compress(self, xf, quantizer, tile_formats):
         if mc.numel_of(xf) == 0:

@@ -53,10 +53,9 @@ class MixedTileThresholdCompression(CompressionAlgorithm):
         assignment, counts_dev = engine.threshold_assign(scores[_METRIC_ROW[self.metric]].contiguous(), order,
                                                          self.metric == "pcc", [self.threshold])
         counts = mc.counts_dict(counts_dev[0])
-        if table is None:
-            table = engine.tile_stats(p, MIXED_TILE_FORMATS)
-        sums = engine.assignment_sums(table, assignment[0])
-        metrics = engine.metrics_from_sums(sums.cpu().numpy(), p.numel)
+        metrics = None                       # float64 recombination only when the caller already has the table
+        if table is not None:
+            metrics = engine.metrics_from_sums(engine.assignment_sums(table, assignment[0]).cpu().numpy(), p.numel)
         return mc.DeviceResult(self.name, p, assignment[0], counts, mc.total_bytes(counts), metrics, list(tile_formats),
                                meta={"scores": scores})
 

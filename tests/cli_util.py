@@ -117,3 +117,43 @@ def compare_trees(got: Path, want: Path) -> list[str]:
             if g.read_text() != w.read_text():
                 diffs.append(f"text differs: {rel}")
     return diffs
+
+
+REF_COPY = ROOT / "oracle" / "_ref"
+
+_DROPIN_DRIVER = r'''
+import contextlib, io, json, os, runpy, sys
+root, ref, work, spec = sys.argv[1:5]
+sys.path.insert(0, root)
+sys.path.insert(0, ref)                      # hf_model_utils (reference, unmodified) + the reference programs
+sys.path.insert(0, os.path.join(ref, "scripts"))
+import quantization_analysis_b200 as q
+q.install_drop_in()                          # quantization_formats / compression_algorithms.* -> this package
+import hf_model_utils as hf
+from tests import cli_util
+hf.build_model_index = cli_util.fake_index_factory(hf, os.path.join(work, "data", "hf-cache"))
+os.chdir(work)
+import time
+for script, argv in json.loads(spec):
+    time.sleep(1.1)                          # the reference names result directories by the second
+    sys.argv = [script] + argv
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            runpy.run_path(script, run_name="__main__")
+    except SystemExit as e:
+        if e.code not in (0, None):
+            print(out.getvalue()[-3000:])
+            raise
+import compression_algorithms, quantization_formats
+assert "quantization_analysis_b200" in compression_algorithms.__file__ and "quantization_analysis_b200" in quantization_formats.__file__
+'''
+
+
+def run_reference_programs_over_dropin(jobs, workdir: Path) -> None:
+    """Run the reference's UNMODIFIED programs (oracle/_ref, made by oracle/make_ref.sh) in a fresh interpreter in which
+    ``quantization_formats`` and ``compression_algorithms`` resolve to this package.  jobs: [(script path, argv), ...]."""
+    import json
+    import subprocess
+    subprocess.run([sys.executable, "-c", _DROPIN_DRIVER, str(ROOT), str(REF_COPY), str(workdir),
+                    json.dumps([[str(s), list(a)] for s, a in jobs])], check=True, cwd=str(workdir), timeout=1200)

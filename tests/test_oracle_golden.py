@@ -143,3 +143,51 @@ def test_fp8_block_dequant_matches_reference_goldens():
         nan = np.isnan(want)
         assert np.array_equal(np.isnan(got), nan)
         assert np.array_equal(got.view(np.uint32)[~nan], want.view(np.uint32)[~nan]), tag
+
+
+def test_restated_whole_tensor_orders_match_numpy():
+    """oracle.np_sdot_f32 / pearson_f32_restated / wq_scores_restated (explicit restatement of NumPy's pairwise sums and
+    OpenBLAS's sdot incl. the 32-element block and the double-accumulated tail) == np.dot / np.mean on this image, for
+    every tail case.  The CUDA scorer is checked against the restatement, so this pins it to the reference's arithmetic."""
+    rng = np.random.default_rng(12)
+    for n in [1, 2, 7, 8, 31, 32, 33, 63, 64, 65, 95, 96, 100, 129, 1000, 1023, 1056, 4113, 10007, 50083, 96 * 160]:
+        x = (rng.standard_normal(n) * 0.02).astype(np.float32)
+        y = orc.quantize(x.reshape(1, -1), "bfp4").reshape(-1)
+        assert np.float32(np.dot(x, y)).view(np.uint32) == np.float32(orc.np_sdot_f32(x, y)).view(np.uint32), n
+        assert orc.pearson_f32(x, y) == orc.pearson_f32_restated(x, y), n
+        d = np.abs(x - y)
+        assert float(np.mean(d)) == orc.wq_scores_restated(x, y)["mae"], n
+
+
+def test_pairwise_plan_reproduces_numpy_add_reduce():
+    """qa_pairwise_plan_build (host side of the C ABI): leaves + tree evaluated in NumPy == np.add.reduce."""
+    from quantization_analysis_b200 import engine
+    rng = np.random.default_rng(1)
+    for n in [1, 5, 8, 100, 128, 129, 257, 1000, 4113, 50083, 1536 * 7]:
+        a = (rng.standard_normal(n) * 0.02).astype(np.float32)
+        plan = engine.pairwise_plan_host(n)
+        nl, lv, nn, ni = (int(v) for v in plan[:4])
+        loff = plan[4:4 + lv + 1]
+        ls = plan[4 + lv + 1:4 + lv + 1 + nl]
+        ll = plan[4 + lv + 1 + nl:4 + lv + 1 + 2 * nl]
+        lf = plan[4 + lv + 1 + 2 * nl:4 + lv + 1 + 2 * nl + ni]
+        rt = plan[4 + lv + 1 + 2 * nl + ni:]
+        assert int(ll.sum()) == n and int(ll.max()) <= 128 and nn == nl + ni
+        v = np.zeros(nn, np.float32)
+        for i in range(nl):
+            v[i] = orc.np_pairwise_sum(a[ls[i] * 8: ls[i] * 8 + ll[i]])
+        for L in range(lv):
+            idx = np.arange(loff[L], loff[L + 1])
+            v[nl + idx] = v[lf[idx]] + v[rt[idx]]
+        assert v[nn - 1] == np.add.reduce(a), n
+
+
+def test_cli_goldens_present_and_strip_times():
+    from tests import cli_util as U
+    for case in U.WQ_CASES:
+        assert (U.CLI_GOLDEN / "wq" / case / "table.txt").exists(), case
+    for case in U.SWEEP_CASES:
+        assert len(list((U.CLI_GOLDEN / "sweep" / case).rglob("sweep_results.csv"))) == 1, case
+    a = "  none  BF16   1.00000  0.000e+00  0.000e+00    0.008  0.000"
+    b = "  none  BF16   1.00000  0.000e+00  0.000e+00    1.234  0.000"
+    assert U.strip_times(a) == U.strip_times(b) and U.strip_times(a) != a
