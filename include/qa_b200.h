@@ -216,7 +216,9 @@ int qa_greedy_assign_par_pre(const double* table, int64_t ntiles, double numel, 
 
 /* Upper bound on the thread-block cluster size of the greedy kernels (1, 2, 4, 8, 16; 0 = automatic: large tensors get
  * 16 CTAs for latency).  A caller with many tensors in flight trades per-tensor latency for SM time with a smaller
- * cluster; results do not depend on the cluster size.  Process-wide; returns the previous value. */
+ * cluster; results do not depend on the cluster size.  The setting belongs to the CALLING THREAD (thread-local): it
+ * applies to the cluster launches that thread enqueues afterwards, so two host threads driving different batches do not
+ * see each other's value.  Returns the previous value. */
 int qa_greedy_cluster_cap(int max_cluster);
 
 /* Diagnostic timeline: device timestamps (ns) {first start, last end} of the cluster kernels since the last reset -

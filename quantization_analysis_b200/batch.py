@@ -367,15 +367,17 @@ class GreedyBatch:
         order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])
         if getattr(self, "_pending", None) is not None:
             cur.wait_event(self._pending)             # a pass still in flight on these buffers goes first
-        prev_cap = _lib.lib().qa_greedy_cluster_cap(self.cluster_cap)
-        for k, i in enumerate(order):
-            st = self.streams[k % len(self.streams)]
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
-                self._enqueue(self.slots[i], st, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
-                self._d2h(self.slots[i])                     # behind this tensor's chain, on its own stream
-        _lib.lib().qa_greedy_cluster_cap(prev_cap)
+        prev_cap = _lib.lib().qa_greedy_cluster_cap(self.cluster_cap)      # thread-local in the library
+        try:
+            for k, i in enumerate(order):
+                st = self.streams[k % len(self.streams)]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
+                    self._enqueue(self.slots[i], st, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
+                    self._d2h(self.slots[i])                     # behind this tensor's chain, on its own stream
+        finally:
+            _lib.lib().qa_greedy_cluster_cap(prev_cap)
         self._pending = torch.cuda.Event()
         if not hasattr(self, "_join_stream"):
             self._join_stream = torch.cuda.Stream(device=self.device)

@@ -29,6 +29,8 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include <mutex>
+
 #include "qa_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -1372,8 +1374,13 @@ __global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restr
 #ifndef QA_CHAIN_MIN_BLOCKS
 #define QA_CHAIN_MIN_BLOCKS 1
 #endif
+#ifdef QA_CHAIN_MAXNREG                    // experiment: cap the chain's registers so tile-stat CTAs can share its SMs
+#define QA_CHAIN_REGCAP __maxnreg__(QA_CHAIN_MAXNREG)
+#else
+#define QA_CHAIN_REGCAP __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS)
+#endif
 template <bool PCC, bool INIT_INLINE>      // INIT_INLINE = false: the init phase ran ahead (greedy_init_kernel); its code is left out
-__global__ void __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS) greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
+__global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,
                                                         double thr, ParOrder ord, qa_pcg64* rng, int8_t* assignment,
                                                         int64_t* counts, double* state, ParWork w, int have_init, int fi_begin,
                                                         int fi_end, int flags) {
@@ -1832,7 +1839,7 @@ static ParWork carve(void* work, int64_t n) {
 }
 
 static int pick_cluster_auto(int64_t n);
-static int g_cluster_cap = 0;       // qa_greedy_cluster_cap: upper bound on the cluster size (0 = none)
+static thread_local int g_cluster_cap = 0;   // qa_greedy_cluster_cap: upper bound on the cluster size (0 = none), per calling thread
 
 static int pick_cluster(int64_t n) {
     const int r = pick_cluster_auto(n);
@@ -1854,16 +1861,37 @@ static int pick_cluster_auto(int64_t n) {
 
 template <typename... KArgs, typename... Args>
 static int launch_cluster_dyn(int dyn, void (*kern)(KArgs...), int nr, cudaStream_t s, Args... args) {
-    {   // attributes are set once per kernel (not a stream operation: keep it out of the per-launch path and of graph captures)
+    {   // attributes are set once per kernel (not a stream operation: keep it out of the per-launch path and of graph
+        // captures); the same moment asks the occupancy calculator whether a 16-CTA cluster can be resident at all, so that
+        // no launch ever has to fail and be retried (a failed launch would invalidate a stream capture)
+        static std::mutex mu;
         static void* done[32];
+        static bool ok16[32];
         static int ndone = 0;
-        bool seen = false;
-        for (int i = 0; i < ndone; ++i) seen = seen || done[i] == (void*)kern;
-        if (!seen) {
+        std::lock_guard<std::mutex> lock(mu);
+        int idx = -1;
+        for (int i = 0; i < ndone; ++i) if (done[i] == (void*)kern) idx = i;
+        if (idx < 0) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-            if (ndone < 32) done[ndone++] = (void*)kern;
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(16, 1, 1);
+            q.blockDim = dim3(GT, 1, 1);
+            q.dynamicSmemBytes = dyn;
+            cudaLaunchAttribute qa_[1];
+            qa_[0].id = cudaLaunchAttributeClusterDimension;
+            qa_[0].val.clusterDim.x = 16;
+            qa_[0].val.clusterDim.y = 1;
+            qa_[0].val.clusterDim.z = 1;
+            q.attrs = qa_;
+            q.numAttrs = 1;
+            int nclusters = 0;
+            const bool fits = cudaOccupancyMaxActiveClusters(&nclusters, kern, &q) == cudaSuccess && nclusters > 0;
+            (void)cudaGetLastError();
+            if (ndone < 32) { done[ndone] = (void*)kern; ok16[ndone] = fits; idx = ndone++; }
+            else if (!fits && nr > 8) nr = 8;
         }
+        if (idx >= 0 && nr > 8 && !ok16[idx]) nr = 8;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(nr, 1, 1);
@@ -1878,10 +1906,6 @@ static int launch_cluster_dyn(int dyn, void (*kern)(KArgs...), int nr, cudaStrea
     cfg.attrs = at;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
-    if (e != cudaSuccess && nr > 8) {           // no GPC can host 16 co-resident CTAs right now: portable size
-        (void)cudaGetLastError();
-        return launch_cluster_dyn(dyn, kern, 8, s, args...);
-    }
     if (e != cudaSuccess) {
         set_error("cluster launch (%d CTAs): %s", nr, cudaGetErrorString(e));
         return 2;

@@ -86,7 +86,11 @@ __device__ __forceinline__ float max3abs(float m, float a, float b) {
 struct GroupAcc {   // in-group float32 partials, two lanes (even / odd element) each
     float2 sy, sy2, sry, sab;
     float mx;
+    double dab;         // QA_SAB_FP64: sum |r| accumulated on the FP64 pipe (exact)
 };
+#ifndef QA_SAB_FP64
+#define QA_SAB_FP64 0
+#endif
 
 template <int F, bool EXACT_ABS>
 __device__ __forceinline__ void fmt_step(const float2 X, const float2 aX, GroupAcc& g) {
@@ -102,6 +106,9 @@ __device__ __forceinline__ void fmt_step(const float2 X, const float2 aX, GroupA
         // |X| - |r|: 0 for elements every format flushes, a short dyadic otherwise (exact in fp32)
         g.sab.x += aX.x - fabsf(r.x);
         g.sab.y += aX.y - fabsf(r.y);
+    } else if (QA_SAB_FP64) {
+        g.dab += fabs((double)r.x);
+        g.dab += fabs((double)r.y);
     } else {
         g.sab.x += fabsf(r.x);
         g.sab.y += fabsf(r.y);
@@ -149,6 +156,7 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
     for (int f = 0; f < 3; ++f) {
         g[f].sy = g[f].sy2 = g[f].sry = g[f].sab = make_float2(0.f, 0.f);
         g[f].mx = 0.f;
+        g[f].dab = 0.0;
     }
     double gx = 0.0, gx2 = 0.0, gax = 0.0;
 #pragma unroll
@@ -178,6 +186,7 @@ __device__ __forceinline__ void group_fast(const uint32_t (&w)[8], TileAcc& a) {
         a.sy2[f] = fma((double)(g[f].sy2.x + g[f].sy2.y), s2, a.sy2[f]);
         a.sxy[f] = fma((double)(g[f].sry.x + g[f].sry.y), s2, a.sxy[f]);   // holds sum r*y; + sum y^2 at tile end
         if (EXACT_ABS) a.sab[f] += fma(-(double)(g[f].sab.x + g[f].sab.y), s1, gax);
+        else if (QA_SAB_FP64) a.sab[f] = fma(g[f].dab, s1, a.sab[f]);
         else a.sab[f] = fma((double)(g[f].sab.x + g[f].sab.y), s1, a.sab[f]);
         a.amax[f] = fmaxf(a.amax[f], g[f].mx * s1f);
     }

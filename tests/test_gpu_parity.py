@@ -681,3 +681,34 @@ def test_greedy_assign_staged_single_tensor_equals_inline(qa):
             torch.cuda.synchronize()
             assert torch.equal(a1, a2) and torch.equal(c1, c2) and torch.equal(r1, r2), (metric, thr, fmts)
             assert torch.equal(s1[:8], s2[:8])
+
+
+def test_greedy_batch_perm_cache_gives_the_same_maps(qa):
+    """GreedyBatch(perm_cache=True): permutations drawn once per (seed, tile count) for the process and shared by every
+    step / list == the per-step prefetch == the oracle; eager, graph replay and end-to-end forms."""
+    from quantization_analysis_b200 import synthetic
+    from quantization_analysis_b200.batch import GreedyBatch
+    shapes = [(256, 512), (96, 320), (256, 512), (64, 64)]
+    xs = [synthetic.randn_bf16_cpu(s, 30 + i) for i, s in enumerate(shapes)]
+    want = []
+    for xb in xs:
+        xf = xb.float().numpy()
+        want.append(orc.greedy_assign(orc.tile_stat_table(xf), list(G.MIXED), "pcc", 0.999, 77))
+    for cache in (False, True, True):          # the second cached batch starts from a warm process-wide cache
+        b = GreedyBatch(shapes, metric="pcc", threshold=0.999, seed=77, perm_cache=cache)
+        b.load_device(xs)
+        b.run()
+        eager = b.collect()
+        b.run_graph()
+        b.run_graph()
+        graph = b.collect()
+        e2e = b.run_from_host([x.pin_memory() for x in xs])
+        for res in (eager, graph, e2e):
+            for r, (a, c) in zip(res, want):
+                assert np.array_equal(r["assignment"], a) and r["counts"] == c, cache
+    two = GreedyBatch(shapes[:2], metric="mae", threshold=3e-4, seed=5, tile_formats=["bfp8", "bfp4"], perm_cache=True)
+    two.load_device(xs[:2])
+    two.run_graph()
+    for r, xb in zip(two.collect(), xs[:2]):
+        a, c = orc.greedy_assign(orc.tile_stat_table(xb.float().numpy()), ["bfp8", "bfp4"], "mae", 3e-4, 5)
+        assert np.array_equal(r["assignment"], a) and r["counts"] == c
