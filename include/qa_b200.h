@@ -143,7 +143,9 @@ int qa_greedy_assign(const double* table, int64_t ntiles, double numel, int metr
  * state[6] = flag bits (bit0 sum x, bit1 sum y of the INITIAL sums of a zero-mean tensor were taken
  * as fixed-order tree sums; bit2 sum y ran on a fixed coarser grid during a pass that could carry
  * it across a binade boundary) + 65536 * speculation rounds; state[7] = final metric value;
- * state[11] = max |x - y| of the final assignment; the rest are cycle counters (profiles/).
+ * state[11] = max |x - y| of the final assignment; state[20] = a lower bound of min |value - thr| / thr over every decision
+ * the chain evaluated (speculative ones included): a caller whose sums may be up to eps away (relative) from the
+ * reference's knows the map is the reference's when state[20] > 2 eps; the rest are cycle counters (profiles/).
  * work: at least qa_greedy_par_work_bytes(n) bytes. */
 int64_t qa_greedy_par_work_bytes(int64_t n);
 int qa_greedy_assign_par(const double* table, int64_t ntiles, double numel, int metric,

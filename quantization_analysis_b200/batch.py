@@ -411,8 +411,14 @@ class GreedyBatch:
         v = sums.numpy()
         if self.metric != "atol":      # state = {sx, sx2, sy, sy2, sxy, sabs, flags, value, cycles x3, max|x-y|, ...}
             v = np.array([v[0], v[1], v[2], v[3], v[4], v[5], v[11]])
-        return {"assignment": a.numpy().reshape(-(-s["rows"] // 32), -(-s["cols"] // 32)).copy(), "counts": counts,
-                "metrics": engine.metrics_from_sums(v, s["numel"]), "state": sums.numpy().copy()}
+        out = {"assignment": a.numpy().reshape(-(-s["rows"] // 32), -(-s["cols"] // 32)).copy(), "counts": counts,
+               "metrics": engine.metrics_from_sums(v, s["numel"]), "state": sums.numpy().copy()}
+        if self.metric != "atol":
+            # certificate inputs (see MixedTileGreedyCompression): flag bits of the initial sums / relaxed grid, and a lower bound
+            # of min |value - thr| / thr over every decision the chain evaluated
+            full = sums.numpy()
+            out["flags"], out["min_margin"] = int(full[6]) & 7, float(full[20])
+        return out
 
     def collect(self) -> list[dict]:
         """Device -> host: assignment maps, counts and exact pcc/mae/atol per tensor (synchronises)."""

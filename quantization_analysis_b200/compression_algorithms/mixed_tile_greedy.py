@@ -26,6 +26,13 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
         self.seed = int(self.params.get("seed", 0))
         self.strict = bool(self.params.get("strict_sums", False))   # extension: NumPy-order float64 tile sums
         self.sequential = bool(self.params.get("sequential_chain", False))  # extension: one-thread decision chain
+        # extension: certify the map.  The cluster kernel reports a lower bound of min |value - thr| / thr over all its decisions
+        # (state[20]); the fast path's sums can differ from the reference's by at most `margin_bound` in relative terms (the
+        # fast tile-stat kernel's sum x^2 is 1e-13-close per tile, the initial sums of zero-mean tensors are tree sums), so a
+        # run whose margin stays above the bound made the reference's decisions.  Below it the tensor is redone with
+        # NumPy-order tile sums and the one-thread reference-order chain.
+        self.certify = bool(self.params.get("certify", True))
+        self.margin_bound = float(self.params.get("margin_bound", 2e-13))
         self.tile_formats = mc.parse_formats(raw) if raw is not None else None
         if self.metric not in mc.VALID_METRICS:
             raise ValueError(f"Unsupported metric: {self.metric}")
@@ -57,11 +64,23 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
                                                                  parallel=False if self.sequential else None)
         else:   # stages overlapped on side streams: same bits, about half the latency
             assignment, counts_dev, state = engine.greedy_assign_staged(table, p.numel, self.metric, self.threshold, tile_formats, rng)
+        cert = {"min_margin": None, "fallback": False}
+        fast = not (self.sequential or self.metric == "atol")
+        if fast:
+            st = state.cpu().numpy()
+            cert["min_margin"], cert["flags"] = float(st[20]), int(st[6]) & 7
+            if self.certify and not self.strict and not (cert["min_margin"] >= self.margin_bound):
+                # a decision closer to the threshold than the sums are to the reference's: reference-order everything
+                cert["fallback"] = True
+                table = engine.tile_stats(p, MIXED_TILE_FORMATS, strict=True)
+                rng = engine.make_rng(seed, p.data.device)
+                assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng,
+                                                                     parallel=False)
         counts = mc.counts_dict(counts_dev)
         sums = engine.assignment_sums(table, assignment)
         metrics = engine.metrics_from_sums(sums.cpu().numpy(), p.numel)
         return mc.DeviceResult(self.name, p, assignment, counts, mc.total_bytes(counts), metrics, list(tile_formats),
-                               meta={"seed": seed, "state": state, "table": table})
+                               meta={"seed": seed, "state": state, "table": table, "certificate": cert})
 
     def _compress(self, xf, quantizer, tile_formats):
         if mc.numel_of(xf) == 0:

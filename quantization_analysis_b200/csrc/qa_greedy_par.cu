@@ -668,9 +668,14 @@ __device__ __noinline__ double pcc_value_cold(double n, double am2, double nmx, 
 __device__ __forceinline__ double pcc_value_par(const Consts& c, double sy, double sy2, double sxy, double sabs) {
     return pcc_value_cold(c.n, c.am2, c.nmx, sy, sy2, sxy, sabs);
 }
-__device__ __forceinline__ bool good_par(const Consts& c, const double (&S)[4]) {
+// `mrg` collects the smallest relative distance of any evaluated decision from the threshold, |value - thr| / thr (for pcc
+// through the gap: (num^2 - K bm2) / (num^2 + K bm2) ~ (value - thr) / thr).  It is taken over every evaluation, speculative
+// ones included, so it is a lower bound of the real minimum: a caller that knows how far its sums may be from the
+// reference's (the fast tile-stat kernel's sum x^2, tree-summed initial sums) can certify the map against it.
+__device__ __forceinline__ bool good_par(const Consts& c, const double (&S)[4], double& mrg) {
     if (c.metric != QA_METRIC_PCC) {
         const double v = c.n != 0.0 ? __ddiv_rn(S[3], c.n) : 0.0;
+        mrg = fmin(mrg, fabs(v - c.thr) / fmax(fabs(c.thr), 1e-300));
         return v <= c.thr;
     }
     if (c.filter_ok) {
@@ -687,13 +692,19 @@ __device__ __forceinline__ bool good_par(const Consts& c, const double (&S)[4]) 
         if (bm2 > ebm2) {
             if (num < -enum_) return false;                                 // certainly negative correlation
             if (num > enum_) {
-                const double gap = num * num - c.K * bm2;
-                const double tol = 2.0 * enum_ * fabs(num) + c.K * ebm2 + 5.7e-14 * (num * num + c.K * bm2);
-                if (fabs(gap) > tol) return gap > 0.0;
+                const double lhs = num * num, rhs = c.K * bm2;
+                const double gap = lhs - rhs;
+                const double tol = 2.0 * enum_ * fabs(num) + c.K * ebm2 + 5.7e-14 * (lhs + rhs);
+                if (fabs(gap) > tol) {
+                    mrg = fmin(mrg, fabs(gap) / (lhs + rhs));
+                    return gap > 0.0;
+                }
             }
         }
     }
-    return pcc_value_par(c, S[0], S[1], S[2], S[3]) >= c.thr;
+    const double v = pcc_value_par(c, S[0], S[1], S[2], S[3]);
+    mrg = fmin(mrg, fabs(v - c.thr) / fmax(fabs(c.thr), 1e-300));
+    return v >= c.thr;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1428,8 +1439,10 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
     const int CHc = c.gth * EPS;
     bool base_failed = false, all_tiles_candidates = true, done = false;
     int accepted_last = nt;
+    double min_margin = 1e300;          // smallest relative distance of an evaluated decision from the threshold (good_par)
     if (!first) {
         const double* r = w.res;
+        min_margin = r[14];
         S[0] = r[0]; S[1] = r[1]; S[2] = r[2]; S[3] = r[3];
         degraded = (unsigned)r[4]; chain_rounds = (unsigned)r[5];
         base_failed = r[6] != 0.0; all_tiles_candidates = r[7] != 0.0; accepted_last = (int)r[8];
@@ -1530,7 +1543,7 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
                         cnd[0] = __dadd_rn(sb0, ra.x); cnd[1] = __dadd_rn(S[1], ra.y); cnd[2] = __dadd_rn(S[2], rb.x);
                         cnd[3] = S[3] + rb.y;
                     } else cnd[3] = __dadd_rn(S[3], rb.y);
-                    return good_par(k, cnd);
+                    return good_par(k, cnd, min_margin);
                 };
                 bool acc = c.gtid < m && passes(c.gtid);              // a sample first: passes that do accept stop here
                 if (!c_any(c, acc)) {
@@ -1556,7 +1569,7 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
         if (base_pass) {
             // every candidate already has this format: the state cannot change, so all of them see the
             // same test (mixed_tile_greedy.py:238-241)
-            if (!good_par(k, S)) {
+            if (!good_par(k, S, min_margin)) {
                 for (int q = c.gtid; q < m; q += c.gth) w.fixed[q] = 1;
                 base_failed = true;
             }
@@ -1647,7 +1660,7 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
                             st_take[s] = cnd[S0 + s];       // kept for the commit (the last element a thread walks)
                         }
                         if (PCC) cnd[3] = S[3] + staged(3, j);          // chunk-start value: only its zero test matters
-                        const bool dj = good_par(k, cnd);
+                        const bool dj = good_par(k, cnd, min_margin);
                         const bool fj = (F >> j) & 1u;
                         D |= dj ? (1u << j) : 0u;
                         if (dj != fj) mism = min(mism, idx);
@@ -1744,6 +1757,7 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
         if (fi + 1 < ord.n) accepted_last = (int)c_reduce_d<false>(c, (double)my_accepts);     // exact: counts < 2^53
         cyc_chain += clock64() - t_mark;
     }
+    min_margin = -c_reduce_d<true>(c, -min_margin);
     if (!last) {
         // hand the running state to the next launch
         c.sync();
@@ -1756,7 +1770,7 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
             r[4] = (double)degraded; r[5] = (double)chain_rounds;
             r[6] = base_failed ? 1.0 : 0.0; r[7] = all_tiles_candidates ? 1.0 : 0.0; r[8] = (double)accepted_last;
             r[9] = (double)cyc_perm; r[10] = (double)cyc_chain; r[11] = done ? 1.0 : 0.0;
-            r[12] = (double)n_chunks; r[13] = (double)n_cutshort;
+            r[12] = (double)n_chunks; r[13] = (double)n_cutshort; r[14] = min_margin;
             stamp(first ? 5 : 7, true);
         }
         return;
@@ -1779,7 +1793,7 @@ __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ tab
         state[12] = (double)c.nr;
         state[13] = (double)cy_load + 1e-9 * 0; state[14] = (double)cy_scan; state[15] = (double)cy_dec;
         state[16] = (double)(clock64() - t_start); state[17] = (double)cy_commit; state[18] = (double)cy_gather;
-        state[19] = (double)n_chunks; state[20] = (double)n_cutshort;
+        state[19] = (double)n_chunks; state[20] = min_margin;     // [20]: lower bound of min |value - thr| / thr over all decisions
         state[13] = w.hdr[8]; state[14] = w.hdr[9]; state[15] = w.hdr[10];
 #ifdef QA_DBG_CHAIN
         printf("chain nt=%d load %lld walk1+scan %lld decide %lld min3 %lld commit %lld gather %lld | chunks %u rounds %u total %lld\n", nt, cy_load, cy_scan, cy_dec, cy_min, cy_commit, cy_gather, n_chunks, chain_rounds, (long long)(clock64() - t_start));

@@ -712,3 +712,37 @@ def test_greedy_batch_perm_cache_gives_the_same_maps(qa):
     for r, xb in zip(two.collect(), xs[:2]):
         a, c = orc.greedy_assign(orc.tile_stat_table(xb.float().numpy()), ["bfp8", "bfp4"], "mae", 3e-4, 5)
         assert np.array_equal(r["assignment"], a) and r["counts"] == c
+
+
+def test_greedy_certificate_margin_and_forced_fallback(qa):
+    """state[20]: lower bound of the smallest relative distance between a decision and the threshold.  A threshold that
+    equals the value reached at some accepted step makes that distance exactly 0: the certified plug-in must notice, redo
+    the tensor in reference order (NumPy-order tile sums + one-thread chain), and still return the reference's map."""
+    ca, eng = qa["ca"], qa["engine"]
+    x = G.algo_input("het_256x512")
+    table_o = orc.tile_stat_table(x)
+    a0 = ca.create_algorithm("mixed-tile-greedy", {"metric": "pcc", "threshold": 0.995, "seed": 3})
+    dr = a0.run_prepared(eng.prepare_tiles(x), list(G.MIXED))
+    cert = dr.meta["certificate"]
+    assert cert["fallback"] is False and cert["min_margin"] > 2e-13 and cert["min_margin"] < 1e-2
+    want, wc = orc.greedy_assign(table_o, list(G.MIXED), "pcc", 0.995, 3)
+    assert np.array_equal(dr.assignment_numpy(), want)
+    # the final state's value is one the chain accepted: use it as the threshold itself
+    tie = float(dr.meta["state"].cpu().numpy()[7])
+    a1 = ca.create_algorithm("mixed-tile-greedy", {"metric": "pcc", "threshold": tie, "seed": 3})
+    dr1 = a1.run_prepared(eng.prepare_tiles(x), list(G.MIXED))
+    assert dr1.meta["certificate"]["min_margin"] < 2e-13 and dr1.meta["certificate"]["fallback"] is True
+    want1, wc1 = orc.greedy_assign(table_o, list(G.MIXED), "pcc", tie, 3)
+    assert np.array_equal(dr1.assignment_numpy(), want1) and dr1.counts == wc1
+    # certify=False keeps the fast result (and still reports the margin)
+    a2 = ca.create_algorithm("mixed-tile-greedy", {"metric": "pcc", "threshold": tie, "seed": 3, "certify": False})
+    dr2 = a2.run_prepared(eng.prepare_tiles(x), list(G.MIXED))
+    assert dr2.meta["certificate"]["fallback"] is False and dr2.meta["certificate"]["min_margin"] < 2e-13
+    # the batch reports the same certificate inputs per tensor
+    from quantization_analysis_b200.batch import GreedyBatch
+    xb = torch.from_numpy(x).to(torch.bfloat16)
+    b = GreedyBatch([x.shape], metric="pcc", threshold=0.995, seed=3)
+    b.load_device([xb])
+    b.run()
+    r = b.collect()[0]
+    assert np.array_equal(r["assignment"], want) and r["min_margin"] == cert["min_margin"] and r["flags"] == cert["flags"]
