@@ -127,6 +127,71 @@ __global__ void __launch_bounds__(256) pw_leaf_kernel(const void* __restrict__ x
     if (lane == 0 && mb) atomicMax(&maxbits[b], mb);
 }
 
+// ---- pairwise leaves, vector form: one thread per leaf, 8 elements (= the 8 strided accumulators) per load --------------
+// Used when every operand is 16-byte aligned at every leaf start (leaf starts are multiples of 8 elements).  YDT == 2: y = 0.
+template <int DT>
+__device__ __forceinline__ void ld8(const void* p, int64_t i, float (&v)[8]) {
+    if (DT == QA_DT_BF16) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p) + i));
+        const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[2 * k] = __uint_as_float(u[k] << 16); v[2 * k + 1] = __uint_as_float(u[k] & 0xFFFF0000u); }
+    } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+template <int XDT, int YDT>
+__global__ void __launch_bounds__(128) pw_leaf_vec_kernel(const void* __restrict__ x, const void* __restrict__ ybase, int64_t y_stride,
+                                                          int64_t nleaves, int64_t nnodes, const int32_t* __restrict__ leaf_start8,
+                                                          const int32_t* __restrict__ leaf_len, float* __restrict__ vals,
+                                                          unsigned* __restrict__ maxbits) {
+    const int b = blockIdx.y;
+    const void* y = YDT == 2 ? nullptr
+                             : (const void*)(reinterpret_cast<const char*>(ybase) + (size_t)b * (size_t)y_stride * (YDT == QA_DT_BF16 ? 2 : 4));
+    float* v = vals + (size_t)b * 3 * nnodes;
+    unsigned mb = 0;
+    for (int64_t leaf = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; leaf < nleaves; leaf += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = (int64_t)leaf_start8[leaf] * 8;
+        const int len = leaf_len[leaf];
+        const int len8 = len - (len & 7);
+        float rx[8], ry[8], rd[8];
+        float sx = 0.f, sy = 0.f, sd = 0.f;
+        if (len8) {
+            for (int i = 0; i < len8; i += 8) {
+                float xv[8], yv[8];
+                ld8<XDT>(x, s + i, xv);
+                if (YDT == 2) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) yv[k] = 0.f;
+                } else ld8<YDT == 2 ? QA_DT_F32 : YDT>(y, s + i, yv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float d = fabsf(__fsub_rn(xv[k], yv[k]));
+                    mb = max(mb, __float_as_uint(d));                     // NaN patterns order above +inf: np.max propagates them
+                    if (i == 0) { rx[k] = xv[k]; ry[k] = yv[k]; rd[k] = d; }
+                    else { rx[k] = __fadd_rn(rx[k], xv[k]); ry[k] = __fadd_rn(ry[k], yv[k]); rd[k] = __fadd_rn(rd[k], d); }
+                }
+            }
+            sx = __fadd_rn(__fadd_rn(__fadd_rn(rx[0], rx[1]), __fadd_rn(rx[2], rx[3])), __fadd_rn(__fadd_rn(rx[4], rx[5]), __fadd_rn(rx[6], rx[7])));
+            sy = __fadd_rn(__fadd_rn(__fadd_rn(ry[0], ry[1]), __fadd_rn(ry[2], ry[3])), __fadd_rn(__fadd_rn(ry[4], ry[5]), __fadd_rn(ry[6], ry[7])));
+            sd = __fadd_rn(__fadd_rn(__fadd_rn(rd[0], rd[1]), __fadd_rn(rd[2], rd[3])), __fadd_rn(__fadd_rn(rd[4], rd[5]), __fadd_rn(rd[6], rd[7])));
+        }
+        for (int i = len < 8 ? 0 : len8; i < len; ++i) {                 // tail (and the n < 8 case) one by one
+            const float xv = ld_elem<XDT>(x, s + i);
+            const float yv = YDT == 2 ? 0.f : ld_elem<YDT == 2 ? QA_DT_F32 : YDT>(y, s + i);
+            const float d = fabsf(__fsub_rn(xv, yv));
+            mb = max(mb, __float_as_uint(d));
+            sx = __fadd_rn(sx, xv); sy = __fadd_rn(sy, yv); sd = __fadd_rn(sd, d);
+        }
+        v[leaf] = sx; v[nnodes + leaf] = sy; v[2 * nnodes + leaf] = sd;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mb = max(mb, __shfl_xor_sync(0xFFFFFFFFu, mb, o));
+    if ((threadIdx.x & 31) == 0 && mb) atomicMax(&maxbits[b], mb);
+}
+
 // ---- pairwise tree: one CTA per batch item, deepest level first -------------------------------------------
 __global__ void __launch_bounds__(1024) pw_tree_kernel(int64_t nleaves, int64_t nnodes, int nlevels, const int32_t* __restrict__ level_off,
                                                        const int32_t* __restrict__ left, const int32_t* __restrict__ right,
@@ -194,6 +259,141 @@ __global__ void __launch_bounds__(64) sdot_kernel(const void* __restrict__ x, co
         float q[4];
 #pragma unroll
         for (int l = 0; l < 4; ++l) q[l] = __fadd_rn(s[l], s[l + 4]);
+        const float kern = __fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3]));
+        float res = kern;
+        if (n1 < n) {
+            double tail = 0.0;
+            for (int64_t j = n1; j < n; ++j) tail = __dadd_rn(tail, (double)__fmul_rn(V(j), U(j)));
+            res = (float)__dadd_rn(tail, (double)kern);
+        }
+        dots[(size_t)b * 4 + kind] = res;
+    }
+}
+
+// ---- sdot chains, pipelined: the 64 chains of one dot product consume elements at one FMA latency per 64 elements, far
+// below what two warps can pull from DRAM with register prefetch (the first version spent ~110 cycles per iteration waiting
+// for loads).  All 256 threads of the block stream 4096-element stages of x and y into a shared-memory ring with cp.async
+// (16 B per request, up to 5 stages = 80 KB in flight); threads 0..63 are the chains and read their operands from there.
+constexpr int SD_TE = 4096;                 // elements per stage (64 chain steps)
+constexpr int SD_THREADS = 256;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+template <int DT>
+__device__ __forceinline__ float lds_elem(const unsigned char* base, int i) {
+    if (DT == QA_DT_BF16) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(base)[i] << 16);
+    return reinterpret_cast<const float*>(base)[i];
+}
+
+// one 4096-element stage of one chain: 64 dependent FMAs; operands are fetched and centred eight steps at a time so that
+// only the FMA chain itself is serial.  ZERO_V: the second operand is the all-zero tensor (fp0).
+template <int UDT, int VDT, bool ZERO_V>
+__device__ __forceinline__ float sd_stage(const unsigned char* su, const unsigned char* sv, int t, float mean_u, float mean_v, float acc) {
+#pragma unroll 1
+    for (int it0 = 0; it0 < SD_TE / 64; it0 += 8) {
+        float u[8], v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i = (it0 + k) * 64 + t;
+            u[k] = lds_elem<UDT>(su, i);
+            v[k] = ZERO_V ? 0.f : lds_elem<VDT>(sv, i);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { u[k] = __fsub_rn(u[k], mean_u); v[k] = __fsub_rn(v[k], mean_v); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = __fmaf_rn(u[k], v[k], acc);
+    }
+    return acc;
+}
+
+template <int XDT, int YDT>      // YDT == 2: y is all zeros (never loaded)
+__global__ void __launch_bounds__(SD_THREADS) sdot_pipe_kernel(const void* __restrict__ x, const void* __restrict__ ybase, int64_t y_stride,
+                                                               int64_t n, int64_t nnodes, int nstages, const float* __restrict__ vals,
+                                                               float* __restrict__ dots) {
+    extern __shared__ __align__(16) unsigned char sd_smem[];
+    const int kind = blockIdx.x;     // 0: (am, am)  1: (bm, bm)  2: (am, bm)
+    const int b = blockIdx.y;
+    if (kind == 0 && b > 0) return;  // x is shared by the batch
+    constexpr int XB = XDT == QA_DT_BF16 ? 2 : 4, YB = YDT == QA_DT_BF16 ? 2 : 4;
+    constexpr bool HAVE_Y = YDT != 2;
+    constexpr int YD = HAVE_Y ? YDT : QA_DT_F32;
+    const unsigned char* xg = reinterpret_cast<const unsigned char*>(x);
+    const unsigned char* yg = HAVE_Y ? reinterpret_cast<const unsigned char*>(ybase) + (size_t)b * (size_t)y_stride * YB : nullptr;
+    const bool need_x = kind != 1, need_y = HAVE_Y && kind != 0;
+    const int stage_bytes = SD_TE * (XB + (HAVE_Y ? YB : 0));
+    const float fn = (float)n;
+    const float mean_x = __fdiv_rn(vals[nnodes - 1], fn);
+    const float mean_y = __fdiv_rn(vals[(size_t)b * 3 * nnodes + nnodes + nnodes - 1], fn);
+    const int t = threadIdx.x;
+    const int64_t n1 = n & ~(int64_t)31, n64 = n1 & ~(int64_t)63;
+    const int64_t ntile = n64 / SD_TE;
+
+    auto issue = [&](int64_t tile) {
+        unsigned char* st = sd_smem + (size_t)(tile % nstages) * stage_bytes;
+        if (need_x)
+            for (int i = t; i < SD_TE * XB / 16; i += SD_THREADS) cp_async16(st + i * 16, xg + (size_t)tile * SD_TE * XB + (size_t)i * 16);
+        if (need_y)
+            for (int i = t; i < SD_TE * YB / 16; i += SD_THREADS)
+                cp_async16(st + SD_TE * XB + i * 16, yg + (size_t)tile * SD_TE * YB + (size_t)i * 16);
+    };
+    for (int p = 0; p < nstages - 1; ++p) {
+        if (p < ntile) issue(p);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    float acc = 0.f;
+    for (int64_t tile = 0; tile < ntile; ++tile) {
+        // stage `tile` has landed once at most nstages - 2 younger groups are pending
+        switch (nstages - 2) {
+            case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+            case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+            case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+            case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+            default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        }
+        __syncthreads();                               // data visible to the chain threads; the stage consumed last round is free
+        if (tile + nstages - 1 < ntile) issue(tile + nstages - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (t < 64) {
+            const unsigned char* st = sd_smem + (size_t)(tile % nstages) * stage_bytes;
+            if (kind == 0) acc = sd_stage<XDT, XDT, false>(st, st, t, mean_x, mean_x, acc);
+            else if (kind == 1) { if (HAVE_Y) acc = sd_stage<YD, YD, false>(st + SD_TE * XB, st + SD_TE * XB, t, mean_y, mean_y, acc); }
+                                                      // y = 0: b - mean(b) = 0 everywhere, the chain stays at 0
+            else acc = HAVE_Y ? sd_stage<XDT, YD, false>(st, st + SD_TE * XB, t, mean_x, mean_y, acc)
+                              : sd_stage<XDT, YD, true>(st, st, t, mean_x, mean_y, acc);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    auto U = [&](int64_t i) -> float {
+        if (kind == 1) return __fsub_rn(HAVE_Y ? ld_elem<YD>(yg, i) : 0.f, mean_y);
+        return __fsub_rn(ld_elem<XDT>(xg, i), mean_x);
+    };
+    auto V = [&](int64_t i) -> float {
+        if (kind == 0) return __fsub_rn(ld_elem<XDT>(xg, i), mean_x);
+        return __fsub_rn(HAVE_Y ? ld_elem<YD>(yg, i) : 0.f, mean_y);
+    };
+    __shared__ float sacc[64];
+    __shared__ float sh[32];
+    if (t < 64) {
+        for (int64_t i = ntile * SD_TE + t; i < n64; i += 64) acc = __fmaf_rn(U(i), V(i), acc);     // < 64 leftover steps
+        sacc[t] = acc;
+    }
+    __syncthreads();
+    if (t < 32) {
+        const int a = t >> 3, l = t & 7;
+        float h = __fadd_rn(sacc[a * 16 + l], sacc[a * 16 + l + 8]);
+        if (n1 - n64 == 32) h = __fmaf_rn(U(n64 + 8 * a + l), V(n64 + 8 * a + l), h);
+        sh[t] = h;
+    }
+    __syncthreads();
+    if (t == 0) {
+        float s8[8];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) s8[l] = __fadd_rn(__fadd_rn(__fadd_rn(sh[l], sh[8 + l]), sh[16 + l]), sh[24 + l]);
+        float q[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) q[l] = __fadd_rn(s8[l], s8[l + 4]);
         const float kern = __fadd_rn(__fadd_rn(q[0], q[1]), __fadd_rn(q[2], q[3]));
         float res = kern;
         if (n1 < n) {
@@ -295,13 +495,40 @@ extern "C" int qa_tensor_scores_f32(const void* x, int x_dtype, const void* y, i
     float* dots = vals + (size_t)nbatch * 3 * nnodes;
     unsigned* maxbits = reinterpret_cast<unsigned*>(dots + (size_t)nbatch * 4);
     cudaMemsetAsync(dots, 0, (size_t)nbatch * 32, s);
-    const int64_t warps_needed = cdiv(nl, 4);
-    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(warps_needed, 8), 148 * 8));
-    pw_leaf_kernel<<<dim3(gx, nbatch), 256, 0, s>>>(x, x_dtype, y, y_dtype, y_stride, nl, nnodes, ls, ll, vals, maxbits);
+    const size_t ybytes = y_dtype == QA_DT_BF16 ? 2 : 4;
+    const bool aligned = reinterpret_cast<uintptr_t>(x) % 32 == 0 &&
+                         (!y || (reinterpret_cast<uintptr_t>(y) % 32 == 0 && ((size_t)y_stride * ybytes) % 32 == 0));
+    if (aligned) {
+        const dim3 gv((unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(nl, 128), 148 * 16)), nbatch);
+        const int yk = y ? y_dtype : 2;
+#define QA_LEAF(XD, YD) pw_leaf_vec_kernel<XD, YD><<<gv, 128, 0, s>>>(x, y, y_stride, nl, nnodes, ls, ll, vals, maxbits)
+        if (x_dtype == QA_DT_BF16) { if (yk == QA_DT_BF16) QA_LEAF(QA_DT_BF16, QA_DT_BF16); else if (yk == QA_DT_F32) QA_LEAF(QA_DT_BF16, QA_DT_F32); else QA_LEAF(QA_DT_BF16, 2); }
+        else { if (yk == QA_DT_BF16) QA_LEAF(QA_DT_F32, QA_DT_BF16); else if (yk == QA_DT_F32) QA_LEAF(QA_DT_F32, QA_DT_F32); else QA_LEAF(QA_DT_F32, 2); }
+#undef QA_LEAF
+    } else {
+        const int64_t warps_needed = cdiv(nl, 4);
+        const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(cdiv(warps_needed, 8), 148 * 8));
+        pw_leaf_kernel<<<dim3(gx, nbatch), 256, 0, s>>>(x, x_dtype, y, y_dtype, y_stride, nl, nnodes, ls, ll, vals, maxbits);
+    }
     if (lv) pw_tree_kernel<<<nbatch, 1024, 0, s>>>(nl, nnodes, lv, loff, lf, rt, vals);
     const dim3 g(3, nbatch);
     const int ydt = y ? y_dtype : QA_DT_F32;
-    if (x_dtype == QA_DT_BF16 && ydt == QA_DT_BF16) sdot_kernel<QA_DT_BF16, QA_DT_BF16><<<g, 64, 0, s>>>(x, y, y_stride, n, nnodes, vals, dots);
+    if (aligned && n >= 4 * (int64_t)SD_TE) {
+        // pipelined chains: shared-memory ring of 4096-element stages
+        const int yk = y ? y_dtype : 2;
+        const int stage_bytes = SD_TE * ((x_dtype == QA_DT_BF16 ? 2 : 4) + (yk == 2 ? 0 : (yk == QA_DT_BF16 ? 2 : 4)));
+        const int nst = std::max(2, std::min(6, 98304 / stage_bytes));
+        const int dyn = nst * stage_bytes;
+#define QA_SDOT(XD, YD)                                                                                              \
+    do {                                                                                                             \
+        static bool attr_done = false;                                                                               \
+        if (!attr_done) { cudaFuncSetAttribute(sdot_pipe_kernel<XD, YD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); attr_done = true; } \
+        sdot_pipe_kernel<XD, YD><<<g, SD_THREADS, dyn, s>>>(x, y, y_stride, n, nnodes, nst, vals, dots);              \
+    } while (0)
+        if (x_dtype == QA_DT_BF16) { if (yk == QA_DT_BF16) QA_SDOT(QA_DT_BF16, QA_DT_BF16); else if (yk == QA_DT_F32) QA_SDOT(QA_DT_BF16, QA_DT_F32); else QA_SDOT(QA_DT_BF16, 2); }
+        else { if (yk == QA_DT_BF16) QA_SDOT(QA_DT_F32, QA_DT_BF16); else if (yk == QA_DT_F32) QA_SDOT(QA_DT_F32, QA_DT_F32); else QA_SDOT(QA_DT_F32, 2); }
+#undef QA_SDOT
+    } else if (x_dtype == QA_DT_BF16 && ydt == QA_DT_BF16) sdot_kernel<QA_DT_BF16, QA_DT_BF16><<<g, 64, 0, s>>>(x, y, y_stride, n, nnodes, vals, dots);
     else if (x_dtype == QA_DT_BF16) sdot_kernel<QA_DT_BF16, QA_DT_F32><<<g, 64, 0, s>>>(x, y, y_stride, n, nnodes, vals, dots);
     else if (ydt == QA_DT_BF16) sdot_kernel<QA_DT_F32, QA_DT_BF16><<<g, 64, 0, s>>>(x, y, y_stride, n, nnodes, vals, dots);
     else sdot_kernel<QA_DT_F32, QA_DT_F32><<<g, 64, 0, s>>>(x, y, y_stride, n, nnodes, vals, dots);
