@@ -11,7 +11,10 @@ Parity pinning: the reference ships no tests or golden vectors,
 so this oracle is pinned against the *reference itself*, imported from
 ``/root/reference`` in the build container by ``tests/golden/make_golden.py``;
 the resulting fixtures are committed under ``tests/golden/`` and re-checked by
-``tests/test_oracle_golden.py`` on every run (CPU).
+``tests/test_oracle_golden.py`` on every run (CPU).  Command-line goldens (``tests/golden/cli``) are the files the
+reference's own ``wq`` and sweep programs wrote (``tests/golden/make_golden_cli.py``).  ``oracle/make_ref.sh`` additionally
+copies the unmodified reference into the git-ignored ``oracle/_ref/`` (it travels to the GPU box): the CPU arm of ``bench.py``
+times it, and ``tests/test_gpu_cli.py`` runs its programs over this repository's drop-in modules.
 
 Third-party arithmetic the reference's results depend on (not vendored in the
 reference; ``requirements.txt`` is unpinned; this image has numpy 2.3.5 with

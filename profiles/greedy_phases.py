@@ -43,7 +43,7 @@ def main():
         for tag, v in (("staged", s), ("inline", s2)):
             print(f"  [{tag}] kcycles: init {v[8]*mhz:.0f} (pos-sums {v[13]*mhz:.0f}, signed {v[14]*mhz:.0f}, rounds {int(v[15])}) "
                   f"perm {v[9]*mhz:.0f} (resolve {v[21]*mhz:.0f}, apply {v[22]*mhz:.0f}, sweeps {int(v[23]) % 65536}, rounds {int(v[23]) // 65536}) "
-                  f"chain {v[10]*mhz:.0f} (gather {v[18]*mhz:.0f}, commit {v[17]*mhz:.0f}, kernel total {v[16]*mhz:.0f}, chunks {int(v[19])}, cut-short {int(v[20])}, "
+                  f"chain {v[10]*mhz:.0f} (gather {v[18]*mhz:.0f}, commit {v[17]*mhz:.0f}, kernel total {v[16]*mhz:.0f}, chunks {int(v[19])}, min margin {v[20]:.2e}, "
                   f"chain rounds {int(v[6]) // 65536}) flags {int(v[6]) % 65536}")
 
 

@@ -41,17 +41,33 @@ def row_stripes(rows: int, world: int) -> list[tuple[int, int]]:
 
 
 def gather_tables(local: torch.Tensor, group=None) -> torch.Tensor:
-    """All-gather per-stripe tables [NSTAT, ntiles_r] into the full table [NSTAT, sum ntiles_r], tile order."""
+    """All-gather per-stripe tables [NSTAT, ntiles_r] into the full table [NSTAT, sum ntiles_r], tile order.
+    One collective for the tile counts and one for the (zero-padded) tables: `all_gather_into_tensor` where the backend has
+    it (NCCL: a single ring/NVLS operation over the whole payload), the list form otherwise (gloo on CPU)."""
     world = dist.get_world_size(group)
     n_local = torch.tensor([local.shape[1]], dtype=torch.int64, device=local.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
+    fused = str(dist.get_backend(group)).lower() == "nccl"     # decided by the backend: the same on every rank
+    if fused:
+        allc = torch.empty(world, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(allc, n_local, group=group)
+        counts = [int(c) for c in allc.tolist()]
+    else:
+        parts_c = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(parts_c, n_local, group=group)
+        counts = [int(c.item()) for c in parts_c]
     width = max(counts)
-    padded = torch.zeros((local.shape[0], width), dtype=local.dtype, device=local.device)
-    padded[:, : local.shape[1]] = local
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded.contiguous(), group=group)
+    if local.shape[1] == width:
+        padded = local.contiguous()
+    else:
+        padded = torch.zeros((local.shape[0], width), dtype=local.dtype, device=local.device)
+        padded[:, : local.shape[1]] = local
+    if fused:
+        out = torch.empty((world,) + tuple(padded.shape), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, padded, group=group)
+        parts = [out[r] for r in range(world)]
+    else:
+        parts = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(parts, padded.contiguous(), group=group)
     return torch.cat([p[:, :c] for p, c in zip(parts, counts)], dim=1).contiguous()
 
 

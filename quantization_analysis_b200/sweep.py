@@ -62,9 +62,11 @@ def _score_maps(p: engine.Prepared, maps: torch.Tensor, rows_idx) -> dict[int, n
 
 
 def sweep_tensor(x, tile_formats=MIXED_TILE_FORMATS, metric: str = "pcc", steps: int = 32, lowest: float = 0.9,
-                 thresholds=None):
+                 thresholds=None, scoring: str = "reference"):
     """-> (rows, maps): rows = list of dicts {threshold (float64), counts, total_bytes, pcc, mae, atol} and the int8 maps
-    [steps, ntiles] in MIXED_TILE_FORMATS numbering."""
+    [steps, ntiles] in MIXED_TILE_FORMATS numbering.  scoring="reference": the reference's float32 whole-tensor values
+    (every distinct map is materialised and scored); "exact": float64 recombination of the tile-stat table, all maps in one
+    launch, no reconstruction (the mathematically exact value of the same formulas)."""
     tile_formats = list(tile_formats)
     p = engine.prepare_tiles(x)
     scores = engine.tile_scores(p, tile_formats)[_ROW[metric]].contiguous()
@@ -77,7 +79,15 @@ def sweep_tensor(x, tile_formats=MIXED_TILE_FORMATS, metric: str = "pcc", steps:
     # the reference recomputes a row only when the assignment differs from the previous step's (sweep:736-742)
     same_as_prev = [False] + [bool(torch.equal(maps[i], maps[i - 1])) for i in range(1, maps.shape[0])]
     distinct = [i for i, s in enumerate(same_as_prev) if not s]
-    sc = _score_maps(p, maps, distinct)
+    if scoring == "exact":
+        table = engine.tile_stats(p, MIXED_TILE_FORMATS)
+        sums = engine.assignment_sums_batch(table, maps).cpu().numpy()
+        sc = {}
+        for i in distinct:
+            m = engine.metrics_from_sums(sums[i], p.numel)
+            sc[i] = (m["pcc"], m["mae"], m["atol"])
+    else:
+        sc = _score_maps(p, maps, distinct)
     rows, last = [], None
     for i, thr in enumerate(thresholds):
         if not same_as_prev[i]:
