@@ -7,7 +7,7 @@ than the 126 MB L2, so no flush is needed).  A step = one pass of the hot path o
 tile statistics, greedy assignment and whole-tensor scoring, per tensor.  With N GPUs every rank runs the same shapes for
 its own layer of the tensor list (weak scaling, no data-path collective; result rows are gathered to rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg1|cfg2|cfg3|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg1|cfg2|cfg3|cfg4|cfg5|cfg2-fp8]
 
 --config selects another of BASELINE.json's configs (same JSON contract; `config.workload` names it):
   cfg1  `none`, formats bf16/bfp8/bfp4/bfp2/fp0 on [1536,7168] (8 rotating buffers > L2), reconstructions + reference scores
@@ -43,6 +43,8 @@ METRICS = {
     "cfg3": "bf16 weight GB/s quantized+scored (mixed-tile-threshold sweep, 32 thresholds, layer-0 attention + dense MLP shapes)",
     "cfg4": "bf16 weight GB/s quantized+scored (mixed-tile-random, 1000 samples per tensor, layer-0 attention + dense MLP shapes)",
     "cfg5": "bf16 weight GB/s quantized+scored (mixed-tile-greedy pcc>=0.999, one MoE layer: 256 experts x gate/up/down)",
+    "cfg2-fp8": "bf16-equivalent weight GB/s quantized+scored (cfg2's tensor list stored as fp8 e4m3fn + 128x128 block scales, "
+                "dequantization fused into the tile-stat read)",
 }
 
 
@@ -231,6 +233,9 @@ def run_reference_arm(args) -> None:
     if rank != 0:
         return
     procs = max(1, os.cpu_count() or 1)
+    metric_key = args.config
+    if args.config == "cfg2-fp8":      # the reference dequantizes on load and then runs cfg2's path on the float32 tensors
+        args.config = "cfg2"
     for _ in range(min(args.warmup, 1)):                         # warm-up is page-cache / import warm only
         cpu_sample_run(args.config, procs)
     vals, t0 = [], time.perf_counter()
@@ -241,7 +246,7 @@ def run_reference_arm(args) -> None:
         vals.append(v)
     wall = time.perf_counter() - t0
     value = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": METRICS[args.config], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    line = {"impl": "reference", "metric": METRICS[metric_key], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
             "scaling": "strong" if args.config == "cfg5" else "weak", "vs_baseline": None,
             "dtype": "f32 values, f64 sums (NumPy)", "data": "synthetic", "config": config_dict(args.config, args.gpus),
@@ -660,6 +665,130 @@ def bench_greedy(args, e) -> None:
 
 
 # --------------------------------------------------------------------------------------------
+# cfg2-fp8: the same tensor list as a real checkpoint stores it - e4m3fn bytes + block scales in,
+# dequantization (hf_model_utils.py:199-215) fused into the tile-stat read.  Not a BASELINE config: one extra line.
+# --------------------------------------------------------------------------------------------
+def bench_fp8(args, e) -> None:
+    torch = e.torch
+    import numpy as np
+    from quantization_analysis_b200 import compression_algorithms as ca, engine, synthetic
+    from quantization_analysis_b200.batch import GreedyBatch
+    W, K = max(3, args.warmup), max(1, args.steps)
+    dev, world, rank = e.dev, e.world, e.rank
+    items = workload(rank)
+    shapes = [s for (_n, s, _sd) in items]
+    host = [tuple(t.pin_memory() for t in synthetic.fp8_checkpoint_cpu(shape, seed)) for (_n, shape, seed) in items]
+    inflight = max(2, INFLIGHT)
+    batches = [GreedyBatch(shapes, **GREEDY, device=dev, perm_cache=True, source="fp8") for _ in range(inflight)]
+    for b in batches:
+        b.load_device(host)
+    torch.cuda.synchronize()
+    for b in batches:
+        b.capture()
+    batch = batches[0]
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(inflight)]
+
+    def run_steps(n_steps: int, lanes_used: int) -> None:
+        cur = torch.cuda.current_stream(dev)
+        for ln in lanes[:lanes_used]:
+            ln.wait_stream(cur)
+        for k in range(n_steps):
+            with torch.cuda.stream(lanes[k % lanes_used]):
+                batches[k % lanes_used].run_graph()
+        for ln in lanes[:lanes_used]:
+            cur.wait_stream(ln)
+
+    def timed(n_steps: int, lanes_used: int) -> float:
+        run_steps(W, lanes_used)
+        e.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e.barrier()
+        a.record()
+        run_steps(n_steps, lanes_used)
+        b.record()
+        e.barrier()
+        return a.elapsed_time(b)
+
+    clk = ClockSampler(e.local, enabled=(rank == 0))
+    clk.__enter__()
+    ms = e.reduce_max(timed(K, inflight))
+    ms_single = e.reduce_max(timed(K, 1)) / K
+    eq_bytes, in_bytes = batch.total_bytes(), batch.input_bytes()
+    value = eq_bytes * world * K / (ms * 1e-3) / 1e9
+    results = batch.collect()
+
+    def e2e_steps(n_steps: int):
+        res = None
+        for k in range(n_steps):
+            b = batches[k % 2]
+            if k >= 2:
+                res = b.finish()
+            b.enqueue_from_host(host)
+        for k in range(min(n_steps, 2)):
+            res = batches[(n_steps - min(n_steps, 2) + k) % 2].finish()
+        return res
+
+    e2e_steps(2)
+    e.barrier()
+    t0 = time.perf_counter()
+    res_e2e = e2e_steps(K)
+    torch.cuda.synchronize()
+    e2e_s = e.reduce_max(time.perf_counter() - t0)
+    clk.__exit__()
+
+    # the tile-stat pass alone (events on the launching stream)
+    for _ in range(2):
+        batch.run_graph(stats=True, assign=False)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        batch.run_graph(stats=True, assign=False)
+    b.record()
+    torch.cuda.synchronize()
+    ms_stats = a.elapsed_time(b) / 5
+    ntiles = sum(s_["ntiles"] for s_ in batch.slots)
+    n_launches = sum(3 if (s_["ntiles"] >= batch.PIPELINE_MIN_TILES and -(-s_["rows"] // 32) >= 8) else 1 for s_ in batch.slots)
+    alg = in_bytes + ntiles * TABLE_BYTES_PER_TILE
+
+    # result check: the two smallest tensors through the plug-in on the reference's dequantized float32 image (strict sums,
+    # one-thread chain: reference order everywhere) give the same maps as the fused fp8 batch
+    algo = ca.create_algorithm("mixed-tile-greedy", dict(GREEDY, strict_sums=True, sequential_chain=True))
+    small = sorted(range(len(items)), key=lambda i: shapes[i][0] * shapes[i][1])[:2]
+    same = True
+    for i in small:
+        x32 = engine.fp8_block_dequant(host[i][0], host[i][1], want_bf16=False)[0].cpu().numpy()
+        r = algo.run(x32, FORMATS5, None, None)[0]
+        same = same and bool(np.array_equal(r.meta["assignment"], results[i]["assignment"])) \
+            and bool(np.array_equal(r.meta["assignment"], res_e2e[i]["assignment"]))
+    if rank == 0:
+        elems = sum(s_["numel"] for s_ in batch.slots)
+        line = {"metric": METRICS["cfg2-fp8"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp8 e4m3fn x f32 block scale in; f32 products + f64 sums", "data": "synthetic",
+                "config": {"workload": "cfg2's tensor list (q_a/q_b/kv_a/kv_b/o_proj) quantized to fp8 e4m3fn with 128x128 block inverse scales "
+                                       "(synthetic randn*0.02); mixed-tile-greedy pcc>=0.999 seed 123; value counts 2 bytes per element (the bf16 "
+                                       "metric's unit) - the pass reads 1 byte per element",
+                           "elements_per_gpu": elems, "input_bytes_per_step": in_bytes, "l2": "inputs_larger_than_l2 (187 MB per step vs 126 MB L2)",
+                           "inflight": f"{inflight} tensor lists in flight", "perm_cache": "on", "parallelism": f"tensor-list x{world}"},
+                "clocks": clk.summary(),
+                "elements_per_s": elems * world * K / (ms * 1e-3),
+                "e2e": {"value": eq_bytes * world * K / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                        "d2h_bytes_per_step": batch.d2h_bytes(), "steps": K, "input_gbs": in_bytes * world * K / e2e_s / 1e9,
+                        "api": "GreedyBatch(source='fp8').enqueue_from_host(pinned e4m3fn bytes + scale grids) / finish() -> maps + pcc/mae/atol on host"},
+                "gpu_launches": batch.launches_per_step * K, "step_latency_ms": ms_single,
+                "roofline": {"bound": "hbm", "kernel": "stats_f32_kernel<fp8>", "achieved": alg / (ms_stats * 1e-3) / 1e9, "peak": e.peak,
+                             "unit": "GB/s", "frac": alg / (ms_stats * 1e-3) / 1e9 / e.peak, "traffic": None, "peak_source": e.peak_src,
+                             "alg_bytes_per_launch": alg / n_launches, "avg_launch_ms": ms_stats / n_launches,
+                             "note": "1 B/elem + scale grid read, 176 B per tile written; the kernel is bound by float32 -> float64 conversions "
+                                     "(seven per element: the reference's float32 product arrays summed in float64), not by HBM"},
+                "cpu_baseline": None,
+                "result_check": {"maps_equal_reference_order_run_on_dequantized_float32": same,
+                                 "counts_first_tensor": results[0]["counts"], "pcc_first_tensor": results[0]["metrics"]["pcc"]}}
+        print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
 # cfg1 / cfg3 / cfg4 through the product API (device tensors in, device results)
 # --------------------------------------------------------------------------------------------
 def bench_other(args, e) -> None:
@@ -779,7 +908,9 @@ def main() -> None:
         run_reference_arm(args)
         return
     e = setup()
-    if args.config in ("cfg2", "cfg5"):
+    if args.config == "cfg2-fp8":
+        bench_fp8(args, e)
+    elif args.config in ("cfg2", "cfg5"):
         bench_greedy(args, e)
     else:
         bench_other(args, e)

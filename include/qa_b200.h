@@ -103,6 +103,26 @@ int qa_tile_stats_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, i
                        uint32_t fmt_mask, int mode, double* table, int64_t tile_row_begin,
                        int64_t tile_row_end, qa_stream_t stream);
 
+/* The fast tile-stat pass for inputs that are NOT bf16-exact - what the reference's loader produces from real checkpoints
+ * (hf_model_utils.py:199-215,271-281: fp8 e4m3fn weights x per-block inverse scales -> float32 with 24-bit significands).
+ * Same table as qa_tile_stats, all four formats (bf16 is a real quantization for these inputs), same lane-owns-a-group
+ * layout; the arithmetic follows quantization_formats.py:121-145 on 24-bit mantissas (alignment shift truncates, then RNE)
+ * and mixed_tile_greedy.py:147-174 (float32 product arrays x*x, x*y, y*y summed in float64).  sum y, sum y^2, sum |x-y| and
+ * max |x-y| equal the reference's NumPy-order float64 sums whenever those are exactly representable; sum x, sum x^2 and
+ * sum x*y of 24-bit data are order-dependent in the last float64 bits (<= 1e-13 relative per tile) - the greedy's decision-margin
+ * certificate (state[20]) covers that, as for the bf16 kernel's sum x^2.  mode: QA_STATS_FAST or QA_STATS_FAST_APPROX_ABS.
+ * Tile rows [tile_row_begin, tile_row_end) are produced (tile_row_end < 0: all), so a large table can be made in pieces. */
+int qa_tile_stats_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, uint32_t fmt_mask, int mode, double* table,
+                      int64_t tile_row_begin, int64_t tile_row_end, qa_stream_t stream);
+
+/* qa_fp8_block_dequant fused into the read of qa_tile_stats_f32: 1 byte per element + the scale grid in, table out; the
+ * float32 image of the tensor is never written.  w_fp8: uint8 [rows, ld]; scale_inv: float32 [scale_rows, scale_cols];
+ * block = ceil(shape / scale shape) (hf_model_utils.py:199-207).  *inexact_count (device, may be NULL; zeroed by the
+ * call that starts at tile row 0) = products that are not bf16-exact. */
+int qa_tile_stats_fp8(const void* w_fp8, const float* scale_inv, int64_t rows, int64_t cols, int64_t ld,
+                      int64_t scale_rows, int64_t scale_cols, uint32_t fmt_mask, int mode, double* table,
+                      int64_t tile_row_begin, int64_t tile_row_end, unsigned long long* inexact_count, qa_stream_t stream);
+
 /* NumPy-float32-faithful per-tile scores on zero-padded 32x32 tiles.
  * Replaces tile_utils.py:46-57 (tile_metrics) incl. metrics.py:6-16 (pearson_corr) with the
  * float32 summation orders of NumPy 2.3.5 / OpenBLAS 0.3.30 SkylakeX.
@@ -225,7 +245,9 @@ int qa_greedy_cluster_cap(int max_cluster);
 
 /* Diagnostic timeline: device timestamps (ns) {first start, last end} of the cluster kernels since the last reset -
  * resolve chain, init sums, chain launch containing pass 0, later chain launch - one row of 8 per cluster-size class
- * (log2 of the cluster size, 0..4).  out8_host: HOST array of 40 (may be NULL); reset != 0 re-arms the slots.  Synchronous (cudaMemcpy{From,To}Symbol). */
+ * (log2 of the cluster size, 0..4).  out8_host: HOST array of 40 (may be NULL); reset != 0 re-arms the slots.  A debugging aid,
+ * the one synchronous entry point (cudaMemcpy{From,To}Symbol), and only live in a library built with -DQA_STAMP_TIMES: the
+ * shipped build compiles the in-kernel timestamps out and this call returns 3. */
 int qa_debug_times(unsigned long long* out8_host, int reset);
 
 /* Diagnostic: cycles per call of the cluster collectives used by qa_greedy_assign_par

@@ -67,7 +67,14 @@ class GreedyBatch:
     PIPELINE_FIRST_TILES = 4096    # ... the first of at least this many tiles (or an eighth of the tensor)
 
     def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
-                 tile_formats=MIXED, n_streams: int | None = None, device=None, perm_cache: bool = False):
+                 tile_formats=MIXED, n_streams: int | None = None, device=None, perm_cache: bool = False,
+                 source: str = "bf16", scale_block=(128, 128)):
+        """source="bf16": resident bf16 tensors (the default).  source="fp8": e4m3fn bytes + a float32 inverse-scale grid per
+        tensor, one scale per `scale_block` elements as checkpoints store them (hf_model_utils.py:199-215); the tile-stat pass
+        dequantizes on the fly (qa_tile_stats_fp8) and everything behind the table is unchanged."""
+        if source not in ("bf16", "fp8"):
+            raise ValueError("source must be 'bf16' or 'fp8'")
+        self.source, self.scale_block = source, (int(scale_block[0]), int(scale_block[1]))
         self.device = device or engine._require_cuda()
         self.perm_cache = bool(perm_cache)
         self.metric, self.threshold, self.seed = metric, float(threshold), int(seed)
@@ -106,7 +113,9 @@ class GreedyBatch:
             self.slots.append({
                 "leader": leader_of[nt],
                 "rows": r, "cols": c, "ntiles": nt, "numel": r * c,
-                "x": torch.empty(r * c, dtype=torch.bfloat16, device=self.device),
+                "x": torch.empty(r * c, dtype=torch.bfloat16 if source == "bf16" else torch.uint8, device=self.device),
+                "scale": None if source == "bf16" else torch.ones((-(-r // self.scale_block[0]), -(-c // self.scale_block[1])),
+                                                                   dtype=torch.float32, device=self.device),
                 "table": torch.zeros((NSTAT, nt), dtype=torch.float64, device=self.device),
                 "assignment": torch.empty(nt, dtype=torch.int8, device=self.device),
                 "counts": torch.zeros(NFMT, dtype=torch.int64, device=self.device),
@@ -159,12 +168,40 @@ class GreedyBatch:
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
-        """Copy bf16 tensors (host or device) into the resident input buffers."""
+        """Copy the inputs (host or device) into the resident buffers: bf16 tensors, or (uint8 e4m3fn bytes, float32 inverse
+        scale grid) pairs for source="fp8"."""
         for slot, t in zip(self.slots, tensors):
+            self._copy_in(slot, t)
+
+    def _copy_in(self, slot, t) -> None:
+        if self.source == "fp8":
+            w, sc = t
+            w = w.view(torch.uint8) if w.dtype != torch.uint8 else w
+            slot["x"].copy_(w.reshape(-1), non_blocking=True)
+            slot["scale"].copy_(sc.reshape(slot["scale"].shape), non_blocking=True)
+        else:
             slot["x"].copy_(t.reshape(-1), non_blocking=True)
 
     def total_bytes(self) -> int:
+        """bf16-equivalent bytes of the weights (2 per element: the unit of BASELINE's metric, whatever the storage format)."""
         return sum(2 * s["numel"] for s in self.slots)
+
+    def input_bytes(self) -> int:
+        """Bytes the tile-stat pass actually reads per step (and an end-to-end step copies to the device)."""
+        if self.source == "fp8":
+            return sum(s["numel"] + 4 * s["scale"].numel() for s in self.slots)
+        return self.total_bytes()
+
+    def _stats(self, slot, mode, lo, hi, sp) -> None:
+        """One tile-stat launch over tile rows [lo, hi) of the slot's table."""
+        L = _lib.lib()
+        if self.source == "fp8":
+            sc = slot["scale"]
+            check(L.qa_tile_stats_fp8(slot["x"].data_ptr(), sc.data_ptr(), slot["rows"], slot["cols"], slot["cols"], sc.shape[0],
+                                      sc.shape[1], 0xF, mode, slot["table"].data_ptr(), lo, hi, None, sp), "qa_tile_stats_fp8")
+        else:
+            check(L.qa_tile_stats_rows(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0xF, mode,
+                                       slot["table"].data_ptr(), lo, hi, sp), "qa_tile_stats_rows")
 
     # ---- compute -------------------------------------------------------------------------
     def _enqueue(self, slot, stream, stats: bool = True, assign: bool = True, side=None) -> None:
@@ -245,21 +282,18 @@ class GreedyBatch:
                 first = max(self.PIPELINE_FIRST_TILES, slot["ntiles"] // 8)       # first cut: about an eighth of the tiles
                 split = max(1, min(tiles_h - 2, -(-first // tiles_w)))
                 split2 = max(split + 1, tiles_h // 2)                      # second cut: half of the tensor
-                sargs = (slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0xF, mode,
-                         slot["table"].data_ptr())
-                check(L.qa_tile_stats_rows(*sargs, 0, split, ss.cuda_stream), "qa_tile_stats_rows")
+                self._stats(slot, mode, 0, split, ss.cuda_stream)
                 slot["ev2"].record(ss)
-                check(L.qa_tile_stats_rows(*sargs, split, split2, ss.cuda_stream), "qa_tile_stats_rows")
+                self._stats(slot, mode, split, split2, ss.cuda_stream)
                 slot["ev3"].record(ss)
-                check(L.qa_tile_stats_rows(*sargs, split2, tiles_h, ss.cuda_stream), "qa_tile_stats_rows")
+                self._stats(slot, mode, split2, tiles_h, ss.cuda_stream)
                 stream.wait_event(slot["ev2"])
                 check(L.qa_greedy_init_sums_range(*iargs, 0, split * tiles_w, sp), "qa_greedy_init_sums_range")
                 stream.wait_event(slot["ev3"])
                 check(L.qa_greedy_init_sums_range(*iargs, split * tiles_w, split2 * tiles_w, sp), "qa_greedy_init_sums_range")
                 split = split2
             else:
-                check(L.qa_tile_stats(slot["x"].data_ptr(), _lib.QA_DT_BF16, slot["rows"], slot["cols"], slot["cols"], 0,
-                                      0xF, mode, slot["table"].data_ptr(), ss.cuda_stream), "qa_tile_stats")
+                self._stats(slot, mode, 0, tiles_h, ss.cuda_stream)
             stream.wait_stream(ss)
             mark("stats")
         if assign:
@@ -360,7 +394,7 @@ class GreedyBatch:
         return out
 
     def enqueue_from_host(self, host_tensors) -> None:
-        """End-to-end pass, asynchronous half: pinned host bf16 -> device, quantize+score+assign, results into pinned host
+        """End-to-end pass, asynchronous half: pinned host bf16 (or fp8 bytes + scale grids) -> device, quantize+score+assign, results into pinned host
         buffers.  Returns immediately; ``finish()`` waits for this pass only, so a caller with two batches can keep the
         PCIe link busy with the next list's inputs while this one computes."""
         cur = torch.cuda.current_stream(self.device)
@@ -373,7 +407,7 @@ class GreedyBatch:
                 st = self.streams[k % len(self.streams)]
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
-                    self.slots[i]["x"].copy_(host_tensors[i].reshape(-1), non_blocking=True)
+                    self._copy_in(self.slots[i], host_tensors[i])
                     self._enqueue(self.slots[i], st, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
                     self._d2h(self.slots[i])                     # behind this tensor's chain, on its own stream
         finally:

@@ -58,7 +58,8 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
         seed = self.seed if seed is None else seed
         if seed == 0:
             seed = secrets.randbits(31)           # mixed_tile_greedy.py:222-224
-        rng = engine.make_rng(seed, p.data.device)
+        dev = table.device
+        rng = engine.make_rng(seed, dev)
         if self.sequential or self.metric == "atol":
             assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng,
                                                                  parallel=False if self.sequential else None)
@@ -73,7 +74,7 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
                 # a decision closer to the threshold than the sums are to the reference's: reference-order everything
                 cert["fallback"] = True
                 table = engine.tile_stats(p, MIXED_TILE_FORMATS, strict=True)
-                rng = engine.make_rng(seed, p.data.device)
+                rng = engine.make_rng(seed, dev)
                 assignment, counts_dev, state = engine.greedy_assign(table, p.numel, self.metric, self.threshold, tile_formats, rng,
                                                                      parallel=False)
         counts = mc.counts_dict(counts_dev)
@@ -81,6 +82,17 @@ class MixedTileGreedyCompression(CompressionAlgorithm):
         metrics = engine.metrics_from_sums(sums.cpu().numpy(), p.numel)
         return mc.DeviceResult(self.name, p, assignment, counts, mc.total_bytes(counts), metrics, list(tile_formats),
                                meta={"seed": seed, "state": state, "table": table, "certificate": cert})
+
+    def run_fp8_blocks(self, w_fp8, scale_inv, formats=None, seed: int | None = None) -> mc.DeviceResult:
+        """Extension for real checkpoints: an fp8 e4m3fn tensor + per-block inverse scales as stored on disk
+        (hf_model_utils.py:199-215,271-281).  The table comes from one pass over the bytes (qa_tile_stats_fp8); the result is what
+        `run` gives on the reference's dequantized float32 tensor."""
+        tile_formats = self.tile_formats or self._filter_from_formats(formats or MIXED_TILE_FORMATS)
+        p = engine.Fp8Prepared(w_fp8, scale_inv)
+        table = None
+        if not self.strict:
+            table, _ = engine.tile_stats_fp8(p.w8, p.scale_inv, MIXED_TILE_FORMATS, exact_abs=(self.metric == "mae"))
+        return self.run_prepared(p, tile_formats, table=table, seed=seed)
 
     def _compress(self, xf, quantizer, tile_formats):
         if mc.numel_of(xf) == 0:

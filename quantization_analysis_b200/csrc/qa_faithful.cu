@@ -270,42 +270,38 @@ __global__ void __launch_bounds__(64) sdot_kernel(const void* __restrict__ x, co
     }
 }
 
-// ---- sdot chains, pipelined: the 64 chains of one dot product consume elements at one FMA latency per 64 elements, far
-// below what two warps can pull from DRAM with register prefetch (the first version spent ~110 cycles per iteration waiting
-// for loads).  All 256 threads of the block stream 4096-element stages of x and y into a shared-memory ring with cp.async
-// (16 B per request, up to 5 stages = 80 KB in flight); threads 0..63 are the chains and read their operands from there.
+// ---- sdot chains, pipelined: the 64 chains of one dot product are sequential by definition (element i feeds chain i % 64 with
+// one fused multiply-add), so the only serial work a chain thread should do is that FFMA: one FMA latency per 64 elements.
+// The block is specialised: all 256 threads stream 4096-element stages of x and y into a shared-memory ring with cp.async
+// (16 B per request, several stages in flight); warps 2..7 "cook" the stage after the one being consumed - unpack, centre
+// (x - mean in float32, the reference's `a - np.mean(a)`) and store (u, v) pairs chain-major into a double-buffered float2
+// stage; warps 0..1 are the 64 chains and per step issue one conflict-free LDS.64 and one FFMA.
 constexpr int SD_TE = 4096;                 // elements per stage (64 chain steps)
 constexpr int SD_THREADS = 256;
+constexpr int SD_COOKED_BYTES = 2 * SD_TE * 8;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
-template <int DT>
-__device__ __forceinline__ float lds_elem(const unsigned char* base, int i) {
-    if (DT == QA_DT_BF16) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(base)[i] << 16);
-    return reinterpret_cast<const float*>(base)[i];
-}
-
-// one 4096-element stage of one chain: 64 dependent FMAs; operands are fetched and centred eight steps at a time so that
-// only the FMA chain itself is serial.  ZERO_V: the second operand is the all-zero tensor (fp0).
-template <int UDT, int VDT, bool ZERO_V>
-__device__ __forceinline__ float sd_stage(const unsigned char* su, const unsigned char* sv, int t, float mean_u, float mean_v, float acc) {
-#pragma unroll 1
-    for (int it0 = 0; it0 < SD_TE / 64; it0 += 8) {
-        float u[8], v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int i = (it0 + k) * 64 + t;
-            u[k] = lds_elem<UDT>(su, i);
-            v[k] = ZERO_V ? 0.f : lds_elem<VDT>(sv, i);
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { u[k] = __fsub_rn(u[k], mean_u); v[k] = __fsub_rn(v[k], mean_v); }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc = __fmaf_rn(u[k], v[k], acc);
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
     }
-    return acc;
+}
+// elements 2i, 2i+1 of a raw stage as float32
+template <int DT>
+__device__ __forceinline__ float2 lds_pair(const unsigned char* base, int i) {
+    if (DT == QA_DT_BF16) {
+        const uint32_t w = reinterpret_cast<const uint32_t*>(base)[i];
+        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+    }
+    return reinterpret_cast<const float2*>(base)[i];
 }
 
 template <int XDT, int YDT>      // YDT == 2: y is all zeros (never loaded)
@@ -323,48 +319,70 @@ __global__ void __launch_bounds__(SD_THREADS) sdot_pipe_kernel(const void* __res
     const unsigned char* yg = HAVE_Y ? reinterpret_cast<const unsigned char*>(ybase) + (size_t)b * (size_t)y_stride * YB : nullptr;
     const bool need_x = kind != 1, need_y = HAVE_Y && kind != 0;
     const int stage_bytes = SD_TE * (XB + (HAVE_Y ? YB : 0));
+    float2* cooked = reinterpret_cast<float2*>(sd_smem);                 // [2][SD_TE] (u, v), element-major = chain-major per step
+    unsigned char* raw = sd_smem + SD_COOKED_BYTES;                      // [nstages][stage_bytes]
     const float fn = (float)n;
     const float mean_x = __fdiv_rn(vals[nnodes - 1], fn);
     const float mean_y = __fdiv_rn(vals[(size_t)b * 3 * nnodes + nnodes + nnodes - 1], fn);
     const int t = threadIdx.x;
     const int64_t n1 = n & ~(int64_t)31, n64 = n1 & ~(int64_t)63;
     const int64_t ntile = n64 / SD_TE;
-
-    auto issue = [&](int64_t tile) {
-        unsigned char* st = sd_smem + (size_t)(tile % nstages) * stage_bytes;
-        if (need_x)
-            for (int i = t; i < SD_TE * XB / 16; i += SD_THREADS) cp_async16(st + i * 16, xg + (size_t)tile * SD_TE * XB + (size_t)i * 16);
-        if (need_y)
-            for (int i = t; i < SD_TE * YB / 16; i += SD_THREADS)
-                cp_async16(st + SD_TE * XB + i * 16, yg + (size_t)tile * SD_TE * YB + (size_t)i * 16);
-    };
-    for (int p = 0; p < nstages - 1; ++p) {
-        if (p < ntile) issue(p);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
     float acc = 0.f;
-    for (int64_t tile = 0; tile < ntile; ++tile) {
-        // stage `tile` has landed once at most nstages - 2 younger groups are pending
-        switch (nstages - 2) {
-            case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-            case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-            case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-            case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-            default: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    if (kind == 1 && !HAVE_Y) {
+        // y = 0: b - mean(b) = 0 everywhere, the chains stay at 0
+    } else {
+        auto issue = [&](int64_t tile) {
+            unsigned char* st = raw + (size_t)(tile % nstages) * stage_bytes;
+            if (need_x)
+                for (int i = t; i < SD_TE * XB / 16; i += SD_THREADS) cp_async16(st + i * 16, xg + (size_t)tile * SD_TE * XB + (size_t)i * 16);
+            if (need_y)
+                for (int i = t; i < SD_TE * YB / 16; i += SD_THREADS)
+                    cp_async16(st + SD_TE * XB + i * 16, yg + (size_t)tile * SD_TE * YB + (size_t)i * 16);
+        };
+        // warps 2..7: raw stage `tile` -> cooked[tile & 1]; thread p of 192 owns element pairs p, p + 192, ...
+        auto cook = [&](int64_t tile) {
+            const unsigned char* st = raw + (size_t)(tile % nstages) * stage_bytes;
+            float4* out = reinterpret_cast<float4*>(cooked + (size_t)(tile & 1) * SD_TE);
+            const float2 nmx = make_float2(-mean_x, -mean_x), nmy = make_float2(-mean_y, -mean_y);
+#pragma unroll 4
+            for (int i = t - 64; i < SD_TE / 2; i += SD_THREADS - 64) {
+                float2 u, v;
+                if (kind == 0) u = v = __fadd2_rn(lds_pair<XDT>(st, i), nmx);
+                else if (kind == 1) u = v = __fadd2_rn(lds_pair<YD>(st + SD_TE * XB, i), nmy);
+                else {
+                    u = __fadd2_rn(lds_pair<XDT>(st, i), nmx);
+                    v = HAVE_Y ? __fadd2_rn(lds_pair<YD>(st + SD_TE * XB, i), nmy) : nmy;      // 0 - mean(b)
+                }
+                out[i] = make_float4(u.x, v.x, u.y, v.y);
+            }
+        };
+        for (int p = 0; p < nstages; ++p) {
+            if (p < ntile) issue(p);
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        __syncthreads();                               // data visible to the chain threads; the stage consumed last round is free
-        if (tile + nstages - 1 < ntile) issue(tile + nstages - 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (t < 64) {
-            const unsigned char* st = sd_smem + (size_t)(tile % nstages) * stage_bytes;
-            if (kind == 0) acc = sd_stage<XDT, XDT, false>(st, st, t, mean_x, mean_x, acc);
-            else if (kind == 1) { if (HAVE_Y) acc = sd_stage<YD, YD, false>(st + SD_TE * XB, st + SD_TE * XB, t, mean_y, mean_y, acc); }
-                                                      // y = 0: b - mean(b) = 0 everywhere, the chain stays at 0
-            else acc = HAVE_Y ? sd_stage<XDT, YD, false>(st, st + SD_TE * XB, t, mean_x, mean_y, acc)
-                              : sd_stage<XDT, YD, true>(st, st, t, mean_x, mean_y, acc);
+        if (ntile > 0) {
+            cp_async_wait_pending(nstages - 1);            // stage 0 has landed
+            __syncthreads();
+            if (t >= 64) cook(0);
         }
+        for (int64_t tile = 0; tile < ntile; ++tile) {
+            cp_async_wait_pending(nstages - 2);            // stage tile + 1 has landed (this thread's part of it)
+            __syncthreads();                               // cooked[tile & 1] is complete, cooked[(tile + 1) & 1] and raw stage `tile` are free
+            if (tile + nstages < ntile) issue(tile + nstages);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (t < 64) {
+                const float2* ck = cooked + (size_t)(tile & 1) * SD_TE + t;
+#pragma unroll 16
+                for (int st = 0; st < SD_TE / 64; ++st) {
+                    const float2 uv = ck[st * 64];
+                    acc = __fmaf_rn(uv.x, uv.y, acc);
+                }
+            } else if (tile + 1 < ntile) {
+                cook(tile + 1);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
     auto U = [&](int64_t i) -> float {
         if (kind == 1) return __fsub_rn(HAVE_Y ? ld_elem<YD>(yg, i) : 0.f, mean_y);
         return __fsub_rn(ld_elem<XDT>(xg, i), mean_x);
@@ -518,11 +536,11 @@ extern "C" int qa_tensor_scores_f32(const void* x, int x_dtype, const void* y, i
         const int yk = y ? y_dtype : 2;
         const int stage_bytes = SD_TE * ((x_dtype == QA_DT_BF16 ? 2 : 4) + (yk == 2 ? 0 : (yk == QA_DT_BF16 ? 2 : 4)));
         const int nst = std::max(2, std::min(6, 98304 / stage_bytes));
-        const int dyn = nst * stage_bytes;
+        const int dyn = SD_COOKED_BYTES + nst * stage_bytes;
 #define QA_SDOT(XD, YD)                                                                                              \
     do {                                                                                                             \
-        static bool attr_done = false;                                                                               \
-        if (!attr_done) { cudaFuncSetAttribute(sdot_pipe_kernel<XD, YD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); attr_done = true; } \
+        if (cudaFuncSetAttribute(sdot_pipe_kernel<XD, YD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_COOKED_BYTES + 98304) != cudaSuccess) \
+            return check_launch("qa_tensor_scores_f32 (shared memory attribute)");                                   \
         sdot_pipe_kernel<XD, YD><<<g, SD_THREADS, dyn, s>>>(x, y, y_stride, n, nnodes, nst, vals, dots);              \
     } while (0)
         if (x_dtype == QA_DT_BF16) { if (yk == QA_DT_BF16) QA_SDOT(QA_DT_BF16, QA_DT_BF16); else if (yk == QA_DT_F32) QA_SDOT(QA_DT_BF16, QA_DT_F32); else QA_SDOT(QA_DT_BF16, 2); }

@@ -48,8 +48,14 @@ constexpr long long M_LO = 1ll << 52, M_HI = 1ll << 53;
 // Diagnostic timeline: first-start / last-end device timestamps (ns, %globaltimer) of the cluster kernels of this file,
 // read back with qa_debug_times.  Slots: 0/1 resolve chain, 2/3 init sums, 4/5 chain launch with pass 0, 6/7 later launch.
 // One row of 8 per cluster-size class (log2 of the cluster size, 0..4), so tensors of different sizes can be told apart.
+// Diagnostic only: compiled in with -DQA_STAMP_TIMES (profiles/step_variants.py); the shipped library does no global
+// atomics of its own in these kernels and qa_debug_times reports "not compiled in".
 __device__ unsigned long long qa_times[5 * 8];
 __device__ __forceinline__ void stamp(int slot, bool is_end) {
+#ifndef QA_STAMP_TIMES
+    (void)slot; (void)is_end;
+    return;
+#endif
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     unsigned nr;
@@ -1943,6 +1949,11 @@ static int launch_cluster_nostage(void (*kern)(KArgs...), int nr, cudaStream_t s
 using namespace qa;
 
 extern "C" int qa_debug_times(unsigned long long* out8_host, int reset) {
+#ifndef QA_STAMP_TIMES
+    (void)out8_host; (void)reset;
+    set_error("qa_debug_times: timestamps are not compiled in (build with -DQA_STAMP_TIMES)");
+    return 3;
+#endif
     if (out8_host && cudaMemcpyFromSymbol(out8_host, qa_times, sizeof(unsigned long long) * 40) != cudaSuccess) return check_launch("qa_debug_times");
     if (reset) {
         unsigned long long init[40];

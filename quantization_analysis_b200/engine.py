@@ -70,6 +70,32 @@ class Prepared:
         return self.tiles_h * self.tiles_w
 
 
+class Fp8Prepared(Prepared):
+    """A 2-D fp8 e4m3fn checkpoint tensor with per-block inverse scales (hf_model_utils.py:199-215).  The tile-stat pass reads
+    the bytes directly (tile_stats_fp8); `data`, the float32 image the reference would have built, is only materialised
+    (qa_fp8_block_dequant) by a consumer that needs it: the reconstruction writer, the strict fallback, the float32 scorer."""
+
+    def __init__(self, w_fp8: torch.Tensor, scale_inv: torch.Tensor):
+        dev = _require_cuda()
+        w = w_fp8.to(dev).contiguous()
+        self.w8 = w.view(torch.uint8) if w.dtype != torch.uint8 else w
+        self.scale_inv = scale_inv.to(dev, torch.float32).contiguous()
+        if self.w8.dim() != 2 or self.scale_inv.dim() != 2:
+            raise ValueError("Fp8Prepared expects 2-D weight and scale tensors")
+        rows, cols = (int(v) for v in self.w8.shape)
+        super().__init__(None, QA_DT_F32, rows, cols, rows * cols, (rows, cols), "nd")
+
+    @property
+    def data(self):
+        if self._data is None:
+            self._data = fp8_block_dequant(self.w8, self.scale_inv, want_bf16=False)[0].reshape(-1)
+        return self._data
+
+    @data.setter
+    def data(self, v):
+        self._data = v
+
+
 def to_device(x, want_bf16: bool = True) -> tuple[torch.Tensor, int]:
     """Host fp32 ndarray / torch tensor -> contiguous device tensor (bf16 when exactly representable)."""
     dev = _require_cuda()
@@ -160,16 +186,39 @@ def quant_recon_cols(x, formats) -> tuple[dict[str, torch.Tensor], tuple]:
 
 
 def tile_stats(p: Prepared, formats=MIXED_FORMATS, strict: bool | None = None, exact_abs: bool = True) -> torch.Tensor:
-    """float64 [NSTAT, ntiles] tile-stat table.  strict=None picks fast for bf16 input.
-    exact_abs=False lets the fast kernel keep sum|x-y| in fp32 group partials (~1e-9 relative):
-    fine when that column only feeds a reported mae or an is-zero test (pcc / atol assignment)."""
-    if strict is None:
-        strict = p.dtype_code != QA_DT_BF16
+    """float64 [NSTAT, ntiles] tile-stat table.  strict=None / False: the fast kernels (qa_tile_stats for bf16 input,
+    qa_tile_stats_f32 for float32 input that is not bf16-exact); strict=True: NumPy-order sums (validation, certificate
+    fallback).  exact_abs=False lets the fast kernels keep sum|x-y| in fp32 group partials (~1e-9 relative): fine when
+    that column only feeds a reported mae or an is-zero test (pcc / atol assignment)."""
     table = torch.zeros((NSTAT, p.ntiles), dtype=torch.float64, device=p.data.device)
     mode = STATS_STRICT if strict else (STATS_FAST if exact_abs else STATS_FAST_APPROX_ABS)
+    if p.dtype_code == QA_DT_F32 and not strict:
+        check(_lib.lib().qa_tile_stats_f32(_ptr(p.data), p.rows, p.cols, p.cols, fmt_mask(formats), mode, _ptr(table), 0, -1,
+                                           _stream()), "qa_tile_stats_f32")
+        return table
     check(_lib.lib().qa_tile_stats(_ptr(p.data), p.dtype_code, p.rows, p.cols, p.cols, p.vec_tail, fmt_mask(formats), mode,
                                    _ptr(table), _stream()), "qa_tile_stats")
     return table
+
+
+def tile_stats_fp8(w_fp8: torch.Tensor, scale_inv: torch.Tensor, formats=MIXED_FORMATS, exact_abs: bool = True):
+    """Tile-stat table straight from fp8 e4m3fn weights + per-block inverse scales (qa_tile_stats_fp8: the dequantization of
+    hf_model_utils.py:199-215 fused into the read; the float32 tensor is never materialised).
+    -> (table float64 [NSTAT, ntiles], number of products that are not bf16-exact as a device int64[1])."""
+    dev = _require_cuda()
+    w = w_fp8.to(dev).contiguous()
+    w8 = w.view(torch.uint8) if w.dtype != torch.uint8 else w
+    sc = scale_inv.to(dev, torch.float32).contiguous()
+    if w8.dim() != 2 or sc.dim() != 2:
+        raise ValueError("tile_stats_fp8 expects 2-D weight and scale tensors")
+    rows, cols = w8.shape
+    ntiles = (-(-rows // TILE)) * (-(-cols // TILE))
+    table = torch.zeros((NSTAT, ntiles), dtype=torch.float64, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+    mode = STATS_FAST if exact_abs else STATS_FAST_APPROX_ABS
+    check(_lib.lib().qa_tile_stats_fp8(_ptr(w8), _ptr(sc), rows, cols, cols, sc.shape[0], sc.shape[1], fmt_mask(formats), mode,
+                                       _ptr(table), 0, -1, _ptr(cnt), _stream()), "qa_tile_stats_fp8")
+    return table, cnt
 
 
 def fp8_block_dequant(w_fp8: torch.Tensor, scale_inv: torch.Tensor, want_bf16: bool = True):

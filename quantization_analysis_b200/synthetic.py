@@ -43,6 +43,24 @@ def randn_bf16_cpu(shape, seed: int, scale: float = 0.02) -> torch.Tensor:
     return (torch.randn(tuple(shape), generator=g, dtype=torch.float32) * scale).to(torch.bfloat16)
 
 
+def fp8_checkpoint_cpu(shape, seed: int, block=(128, 128), scale: float = 0.02):
+    """A 2-D weight as an fp8 checkpoint stores it (what hf_model_utils.py:199-215 dequantizes): randn * scale quantized per
+    `block` to e4m3fn with inverse scale = block amax / 448.  -> (uint8 [rows, cols] e4m3fn bytes, float32 [ceil(rows / block
+    rows), ceil(cols / block cols)] inverse scales)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    rows, cols = (int(v) for v in shape)
+    x = torch.randn((rows, cols), generator=g, dtype=torch.float32) * scale
+    br, bc = block
+    sr, scn = -(-rows // br), -(-cols // bc)
+    pad = torch.zeros((sr * br, scn * bc), dtype=torch.float32)
+    pad[:rows, :cols] = x
+    amax = pad.reshape(sr, br, scn, bc).abs().amax(dim=(1, 3)).clamp_min(1e-12)
+    inv = (amax / 448.0).to(torch.float32)
+    q = (pad.reshape(sr, br, scn, bc) / inv[:, None, :, None]).reshape(sr * br, scn * bc)[:rows, :cols]
+    return q.to(torch.float8_e4m3fn).view(torch.uint8).contiguous(), inv.contiguous()
+
+
 def randn_f32_np(shape, seed: int, scale: float = 0.02) -> np.ndarray:
     """Same values as float32 NumPy (bf16-exact)."""
     return randn_bf16_cpu(shape, seed, scale).to(torch.float32).numpy()

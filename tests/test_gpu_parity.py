@@ -444,7 +444,8 @@ def test_metrics_api_matches_fp64_formulas(qa):
 
 def test_fp32_inputs_take_the_general_path(qa):
     """Non-bf16-exact float32 tensors (what a dequantised fp8 checkpoint looks like, hf_model_utils.py:209-215):
-    never truncated - strict NumPy-order stats, faithful tile scores, greedy / threshold maps all match the oracle."""
+    never truncated - strict NumPy-order stats, faithful tile scores, greedy / threshold maps all match the oracle (the greedy
+    runs on the fast float32 table, qa_tile_stats_f32, under the decision-margin certificate)."""
     eng, ca = qa["engine"], qa["ca"]
     rng = np.random.default_rng(17)
     x = (rng.standard_normal((96, 200)) * 0.02).astype(np.float32)
@@ -452,7 +453,7 @@ def test_fp32_inputs_take_the_general_path(qa):
     p = eng.prepare_tiles(x)
     assert p.dtype_code == 1                                   # stayed float32
     want = orc.tile_stat_table(x)
-    got = _table_from_device(eng.tile_stats(p, G.MIXED), None)  # strict is selected automatically
+    got = _table_from_device(eng.tile_stats(p, G.MIXED, strict=True), None)
     assert np.array_equal(got["sx"], want["sx"]) and np.array_equal(got["sx2"], want["sx2"])
     for f in G.MIXED:
         for k in ("sy", "sy2", "sxy", "sabs", "amax"):
@@ -746,3 +747,115 @@ def test_greedy_certificate_margin_and_forced_fallback(qa):
     b.run()
     r = b.collect()[0]
     assert np.array_equal(r["assignment"], want) and r["min_margin"] == cert["min_margin"] and r["flags"] == cert["flags"]
+
+
+def _check_f32_fast_table(got, want, tag, exact=True):
+    """qa_tile_stats_f32 / qa_tile_stats_fp8 against the NumPy-order oracle: sums of exactly representable terms are bit-equal;
+    sum x, sum x^2 and sum x*y of 24-bit data round differently in another order (held to 1e-13 relative, a few ulp).
+    exact=False: a tensor whose tiles span ~40 octaves - no float64 tile sum is exactly representable, all are order-dependent."""
+    for k in ("sx", "sx2"):
+        assert np.allclose(got[k], want[k], rtol=1e-13, atol=0, equal_nan=True), (tag, k)
+    for f in G.MIXED:
+        for k in ("sy", "sy2", "sabs", "amax"):
+            if exact or k == "amax":
+                assert np.array_equal(got[f][k], want[f][k], equal_nan=True), (tag, f, k)
+            else:
+                assert np.allclose(got[f][k], want[f][k], rtol=1e-13, atol=1e-300, equal_nan=True), (tag, f, k)
+        assert np.allclose(got[f]["sxy"], want[f]["sxy"], rtol=1e-13, atol=0, equal_nan=True), (tag, f)
+
+
+def test_fast_tile_stats_for_float32_inputs(qa):
+    """The fast tile-stat kernel for inputs that are not bf16-exact (24-bit significands: the alignment shift truncates before the
+    round, products are float32 arrays) on normal, heavy-tailed, tiny, denormal-bearing, ragged and 1-D tensors."""
+    eng = qa["engine"]
+    rng = np.random.default_rng(23)
+    cases = {
+        "normal": (rng.standard_normal((96, 200)) * 0.02).astype(np.float32),
+        "heavy": (rng.standard_t(2, (64, 544)) * 0.05).astype(np.float32),
+        "ragged": rng.standard_normal((45, 77)).astype(np.float32),
+        "vector": rng.standard_normal(1000).astype(np.float32),
+        "tiny": (rng.standard_normal((32, 64)) * 1e-22).astype(np.float32),
+        "wide": (rng.standard_normal((64, 64)) * np.exp2(rng.integers(-30, 10, (64, 64)))).astype(np.float32),
+    }
+    cases["normal"][5, 7] = 0.0
+    cases["wide"][3, :16] = 0.0
+    cases["wide"][4, 16:32] = np.float32(1e-41)          # a denormal-only group
+    cases["wide"][9, 40] = np.float32(3e-39)
+    for tag, x in cases.items():
+        p = eng.prepare_tiles(x)
+        assert p.dtype_code == 1, tag
+        want = orc.tile_stat_table(x)
+        for exact_abs in (True, False):
+            got = _table_from_device(eng.tile_stats(p, G.MIXED, exact_abs=exact_abs), None)
+            if not exact_abs:            # fp32 group partials of sum |x-y|: close, not exact
+                for f in G.MIXED:
+                    assert np.allclose(got[f]["sabs"], want[f]["sabs"], rtol=1e-6, atol=0), (tag, f)
+                    got[f]["sabs"] = want[f]["sabs"]
+            _check_f32_fast_table(got, want, tag, exact=(tag != "wide"))
+        # piecewise production of the same table
+        if p.tiles_h >= 2:
+            whole = eng.tile_stats(p, G.MIXED)
+            from quantization_analysis_b200 import _lib
+            t2 = torch.zeros_like(whole)
+            for lo, hi in ((0, 1), (1, p.tiles_h)):
+                _lib.check(_lib.lib().qa_tile_stats_f32(p.data.data_ptr(), p.rows, p.cols, p.cols, 0xF, 0, t2.data_ptr(), lo, hi,
+                                                        torch.cuda.current_stream().cuda_stream), "qa_tile_stats_f32")
+            assert torch.equal(whole, t2), tag
+
+
+def test_fp8_fused_tile_stats_and_greedy(qa):
+    """qa_tile_stats_fp8 (e4m3fn bytes + block scales in, table out) == the float32 kernel on the dequantized tensor, bit for
+    bit, and == the oracle on the reference's dequantization goldens; the greedy map from the fused table is the oracle's."""
+    eng, ca = qa["engine"], qa["ca"]
+    z = G.npz("fp8_dequant.npz")
+    w, s = z["rag__w"], z["rag__s"]                       # 300 x 520 with 100 x 104 blocks: groups straddle scale blocks
+    xf = z["rag__out"].view(np.float32).reshape(w.shape)
+    table, cnt = eng.tile_stats_fp8(torch.from_numpy(w), torch.from_numpy(s))
+    assert int(cnt.item()) == int(((xf.view(np.uint32) & 0xFFFF) != 0).sum())
+    p = eng.prepare_tiles(xf)
+    if p.dtype_code == 1:
+        assert torch.equal(table.nan_to_num(nan=-1.0), eng.tile_stats(p, G.MIXED).nan_to_num(nan=-1.0))
+    with np.errstate(all="ignore"):
+        want = orc.tile_stat_table(xf)
+    # uniformly random bytes span all 17 octaves of e4m3 inside a tile: no float64 tile sum is exactly representable
+    _check_f32_fast_table(_table_from_device(table, None), want, "rag", exact=False)
+    # a checkpoint-like tensor: randn * 0.02 quantized per 128 x 128 block to e4m3fn (amax / 448 inverse scales)
+    from quantization_analysis_b200 import synthetic
+    rng = np.random.default_rng(5)
+    wt, sct = synthetic.fp8_checkpoint_cpu((512, 1024), 5)
+    w, sc = wt.numpy(), sct.numpy()
+    out, _, bad = eng.fp8_block_dequant(torch.from_numpy(w), torch.from_numpy(sc), want_bf16=False)
+    assert bad > 0
+    x = out.cpu().numpy()
+    table, _ = eng.tile_stats_fp8(torch.from_numpy(w), torch.from_numpy(sc), exact_abs=False)
+    want = orc.tile_stat_table(x)
+    got = _table_from_device(table, None)
+    for f in G.MIXED:
+        assert np.allclose(got[f]["sabs"], want[f]["sabs"], rtol=1e-6, atol=0)
+        got[f]["sabs"] = want[f]["sabs"]
+    _check_f32_fast_table(got, want, "ckpt")
+    algo = ca.create_algorithm("mixed-tile-greedy", {"metric": "pcc", "threshold": 0.999, "seed": 9})
+    dr = algo.run_fp8_blocks(torch.from_numpy(w), torch.from_numpy(sc), list(G.MIXED))
+    a, counts = orc.greedy_assign(want, list(G.MIXED), "pcc", 0.999, 9)
+    assert np.array_equal(dr.assignment_numpy(), a) and dr.counts == counts
+    assert dr.meta["certificate"]["fallback"] is False
+    assert np.array_equal(G.bits(eng.result_to_numpy(dr.prepared, dr.y_device())), G.bits(orc.apply_assignment(x, a)))
+    # the batched schedule on fp8 sources (graph replay and the host -> device form): same maps
+    from quantization_analysis_b200.batch import GreedyBatch
+    w2 = rng.integers(0, 256, (1100, 2048), dtype=np.uint8)        # 35 x 64 tiles: the pipelined three-range table
+    w2[(w2 & 0x7F) == 0x7F] = 0x3C
+    sc2 = np.exp(rng.uniform(np.log(1e-4), np.log(3e-3), (9, 16))).astype(np.float32)
+    srcs = [(torch.from_numpy(w), torch.from_numpy(sc)), (torch.from_numpy(w2), torch.from_numpy(sc2))]
+    b = GreedyBatch([(512, 1024), (1100, 2048)], metric="pcc", threshold=0.999, seed=9, source="fp8", perm_cache=True)
+    b.PIPELINE_MIN_TILES = 2048
+    b.load_device(srcs)
+    b.run_graph()
+    res = b.collect()
+    x2 = eng.fp8_block_dequant(*srcs[1], want_bf16=False)[0].cpu().numpy()
+    a2, c2 = orc.greedy_assign(orc.tile_stat_table(x2), list(G.MIXED), "pcc", 0.999, 9)
+    assert np.array_equal(res[0]["assignment"], a) and res[0]["counts"] == counts
+    assert np.array_equal(res[1]["assignment"], a2) and res[1]["counts"] == c2
+    assert b.input_bytes() == 512 * 1024 + 1100 * 2048 + 4 * (4 * 8 + 9 * 16)
+    pinned = [(t.pin_memory(), s_.pin_memory()) for t, s_ in srcs]
+    res = b.run_from_host(pinned)
+    assert np.array_equal(res[1]["assignment"], a2) and res[0]["counts"] == counts
