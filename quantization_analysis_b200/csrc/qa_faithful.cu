@@ -270,45 +270,74 @@ __global__ void __launch_bounds__(64) sdot_kernel(const void* __restrict__ x, co
     }
 }
 
-// ---- sdot chains, pipelined: the 64 chains of one dot product are sequential by definition (element i feeds chain i % 64 with
-// one fused multiply-add), so the only serial work a chain thread should do is that FFMA: one FMA latency per 64 elements.
-// The block is specialised: all 256 threads stream 4096-element stages of x and y into a shared-memory ring with cp.async
-// (16 B per request, several stages in flight); warps 2..7 "cook" the stage after the one being consumed - unpack, centre
-// (x - mean in float32, the reference's `a - np.mean(a)`) and store (u, v) pairs chain-major into a double-buffered float2
-// stage; warps 0..1 are the 64 chains and per step issue one conflict-free LDS.64 and one FFMA.
+// ---- sdot chains, pipelined.  The 64 chains of one dot product are sequential by definition (element i feeds chain i % 64 with
+// one fused multiply-add), so a dot product is one CTA of 64 threads whatever the tensor size, and the job is to keep those two
+// warps issuing nothing but the chain's own work: LDS, unpack, centre (x - mean in float32, the reference's `a - np.mean(a)`),
+// FFMA - seven instructions per element for a bf16 pair.  Operands arrive through the TMA engine: thread 0 issues one bulk copy
+// (cp.async.bulk, 8 - 16 KB) per operand and 4096-element stage into a shared-memory ring and every stage completes on its own
+// mbarrier, so no warp spends issue slots on address arithmetic or per-16-byte copy requests, and up to eight stages are in
+// flight.  Measured per SM on o_proj-size operands: LDGSTS (cp.async) streaming sustains 38 GB/s = 840 cycles per bf16-pair
+// stage, the bulk copies 56 GB/s = 570 cycles, the chains themselves 1 250 cycles (see sd_stage): 33 -> 20 ms per call.
 constexpr int SD_TE = 4096;                 // elements per stage (64 chain steps)
-constexpr int SD_THREADS = 256;
-constexpr int SD_COOKED_BYTES = 2 * SD_TE * 8;
+constexpr int SD_MAX_STAGES = 8;
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SD_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SD_DONE;\n\t"
+        "bra SD_WAIT;\n\t"
+        "SD_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_pending(int pending) {
-    switch (pending) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    }
-}
-// elements 2i, 2i+1 of a raw stage as float32
 template <int DT>
-__device__ __forceinline__ float2 lds_pair(const unsigned char* base, int i) {
-    if (DT == QA_DT_BF16) {
-        const uint32_t w = reinterpret_cast<const uint32_t*>(base)[i];
-        return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+__device__ __forceinline__ float lds_elem(const unsigned char* base, int i) {
+    if (DT == QA_DT_BF16) return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(base)[i] << 16);
+    return reinterpret_cast<const float*>(base)[i];
+}
+
+// One 4096-element stage of one chain: 64 dependent FFMAs; the operands of the next 16 steps are requested before the chain
+// runs through the present 16.  SAME: both operands are the same tensor (a.a, b.b); ZERO_V: the second operand is all zeros
+// (fp0).  Measured (profiles/r2_scorer_time.txt): 18 - 20 cycles per step for a bf16 pair - a lone warp per SM sub-partition
+// issues its seven instructions per step at about one every two cycles, and ptxas keeps only ~6 shared-memory loads in flight
+// (one per scoreboard), whatever order the source asks for (an explicit volatile-asm pipeline compiled to the same schedule).
+template <int UDT, int VDT, bool SAME, bool ZERO_V>
+__device__ __forceinline__ float sd_stage(const unsigned char* su, const unsigned char* sv, int t, float mean_u, float mean_v, float acc) {
+    constexpr int BL = 16;
+    float ru[BL], rv[BL];
+#pragma unroll
+    for (int k = 0; k < BL; ++k) {
+        ru[k] = lds_elem<UDT>(su, k * 64 + t);
+        rv[k] = (SAME || ZERO_V) ? 0.f : lds_elem<VDT>(sv, k * 64 + t);
     }
-    return reinterpret_cast<const float2*>(base)[i];
+#pragma unroll
+    for (int blk = 0; blk < SD_TE / 64 / BL; ++blk) {
+        float u[BL], v[BL];
+#pragma unroll
+        for (int k = 0; k < BL; ++k) {
+            u[k] = __fsub_rn(ru[k], mean_u);
+            v[k] = SAME ? u[k] : __fsub_rn(rv[k], mean_v);
+        }
+        if (blk + 1 < SD_TE / 64 / BL) {
+#pragma unroll
+            for (int k = 0; k < BL; ++k) {
+                ru[k] = lds_elem<UDT>(su, ((blk + 1) * BL + k) * 64 + t);
+                rv[k] = (SAME || ZERO_V) ? 0.f : lds_elem<VDT>(sv, ((blk + 1) * BL + k) * 64 + t);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < BL; ++k) acc = __fmaf_rn(u[k], v[k], acc);
+    }
+    return acc;
 }
 
 template <int XDT, int YDT>      // YDT == 2: y is all zeros (never loaded)
-__global__ void __launch_bounds__(SD_THREADS) sdot_pipe_kernel(const void* __restrict__ x, const void* __restrict__ ybase, int64_t y_stride,
-                                                               int64_t n, int64_t nnodes, int nstages, const float* __restrict__ vals,
-                                                               float* __restrict__ dots) {
-    extern __shared__ __align__(16) unsigned char sd_smem[];
+__global__ void __launch_bounds__(64, 1) sdot_pipe_kernel(const void* __restrict__ x, const void* __restrict__ ybase, int64_t y_stride, int64_t n,
+                                                       int64_t nnodes, int nstages, const float* __restrict__ vals,
+                                                       float* __restrict__ dots) {
+    extern __shared__ __align__(128) unsigned char sd_smem[];
+    __shared__ __align__(8) unsigned long long full[SD_MAX_STAGES];
     const int kind = blockIdx.x;     // 0: (am, am)  1: (bm, bm)  2: (am, bm)
     const int b = blockIdx.y;
     if (kind == 0 && b > 0) return;  // x is shared by the batch
@@ -319,8 +348,6 @@ __global__ void __launch_bounds__(SD_THREADS) sdot_pipe_kernel(const void* __res
     const unsigned char* yg = HAVE_Y ? reinterpret_cast<const unsigned char*>(ybase) + (size_t)b * (size_t)y_stride * YB : nullptr;
     const bool need_x = kind != 1, need_y = HAVE_Y && kind != 0;
     const int stage_bytes = SD_TE * (XB + (HAVE_Y ? YB : 0));
-    float2* cooked = reinterpret_cast<float2*>(sd_smem);                 // [2][SD_TE] (u, v), element-major = chain-major per step
-    unsigned char* raw = sd_smem + SD_COOKED_BYTES;                      // [nstages][stage_bytes]
     const float fn = (float)n;
     const float mean_x = __fdiv_rn(vals[nnodes - 1], fn);
     const float mean_y = __fdiv_rn(vals[(size_t)b * 3 * nnodes + nnodes + nnodes - 1], fn);
@@ -331,57 +358,44 @@ __global__ void __launch_bounds__(SD_THREADS) sdot_pipe_kernel(const void* __res
     if (kind == 1 && !HAVE_Y) {
         // y = 0: b - mean(b) = 0 everywhere, the chains stay at 0
     } else {
+        if (t == 0) {
+            for (int s_ = 0; s_ < nstages; ++s_) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s_])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncthreads();
+        // thread 0: arm the stage's barrier with its byte count, then one bulk copy per operand
         auto issue = [&](int64_t tile) {
-            unsigned char* st = raw + (size_t)(tile % nstages) * stage_bytes;
+            const int slot = (int)(tile % nstages);
+            const unsigned bar = smem_u32(&full[slot]);
+            unsigned char* st = sd_smem + (size_t)slot * stage_bytes;
+            const unsigned bytes = (need_x ? SD_TE * XB : 0) + (need_y ? SD_TE * YB : 0);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             if (need_x)
-                for (int i = t; i < SD_TE * XB / 16; i += SD_THREADS) cp_async16(st + i * 16, xg + (size_t)tile * SD_TE * XB + (size_t)i * 16);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(st)),
+                             "l"(xg + (size_t)tile * SD_TE * XB), "r"((unsigned)(SD_TE * XB)), "r"(bar)
+                             : "memory");
             if (need_y)
-                for (int i = t; i < SD_TE * YB / 16; i += SD_THREADS)
-                    cp_async16(st + SD_TE * XB + i * 16, yg + (size_t)tile * SD_TE * YB + (size_t)i * 16);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(st + SD_TE * XB)),
+                             "l"(yg + (size_t)tile * SD_TE * YB), "r"((unsigned)(SD_TE * YB)), "r"(bar)
+                             : "memory");
         };
-        // warps 2..7: raw stage `tile` -> cooked[tile & 1]; thread p of 192 owns element pairs p, p + 192, ...
-        auto cook = [&](int64_t tile) {
-            const unsigned char* st = raw + (size_t)(tile % nstages) * stage_bytes;
-            float4* out = reinterpret_cast<float4*>(cooked + (size_t)(tile & 1) * SD_TE);
-            const float2 nmx = make_float2(-mean_x, -mean_x), nmy = make_float2(-mean_y, -mean_y);
-#pragma unroll 4
-            for (int i = t - 64; i < SD_TE / 2; i += SD_THREADS - 64) {
-                float2 u, v;
-                if (kind == 0) u = v = __fadd2_rn(lds_pair<XDT>(st, i), nmx);
-                else if (kind == 1) u = v = __fadd2_rn(lds_pair<YD>(st + SD_TE * XB, i), nmy);
-                else {
-                    u = __fadd2_rn(lds_pair<XDT>(st, i), nmx);
-                    v = HAVE_Y ? __fadd2_rn(lds_pair<YD>(st + SD_TE * XB, i), nmy) : nmy;      // 0 - mean(b)
-                }
-                out[i] = make_float4(u.x, v.x, u.y, v.y);
-            }
-        };
-        for (int p = 0; p < nstages; ++p) {
-            if (p < ntile) issue(p);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        if (ntile > 0) {
-            cp_async_wait_pending(nstages - 1);            // stage 0 has landed
-            __syncthreads();
-            if (t >= 64) cook(0);
-        }
+        if (t == 0)
+            for (int p = 0; p < nstages && p < ntile; ++p) issue(p);
+        int slot = 0;
+        unsigned parity = 0;
         for (int64_t tile = 0; tile < ntile; ++tile) {
-            cp_async_wait_pending(nstages - 2);            // stage tile + 1 has landed (this thread's part of it)
-            __syncthreads();                               // cooked[tile & 1] is complete, cooked[(tile + 1) & 1] and raw stage `tile` are free
-            if (tile + nstages < ntile) issue(tile + nstages);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            if (t < 64) {
-                const float2* ck = cooked + (size_t)(tile & 1) * SD_TE + t;
-#pragma unroll 16
-                for (int st = 0; st < SD_TE / 64; ++st) {
-                    const float2 uv = ck[st * 64];
-                    acc = __fmaf_rn(uv.x, uv.y, acc);
-                }
-            } else if (tile + 1 < ntile) {
-                cook(tile + 1);
-            }
+            mbar_wait(smem_u32(&full[slot]), parity);      // the stage's bytes have landed
+            const unsigned char* st = sd_smem + (size_t)slot * stage_bytes;
+            if (kind == 0) acc = sd_stage<XDT, XDT, true, false>(st, st, t, mean_x, mean_x, acc);
+            else if (kind == 1) acc = sd_stage<YD, YD, true, false>(st + SD_TE * XB, st + SD_TE * XB, t, mean_y, mean_y, acc);
+            else acc = HAVE_Y ? sd_stage<XDT, YD, false, false>(st, st + SD_TE * XB, t, mean_x, mean_y, acc)
+                              : sd_stage<XDT, YD, false, true>(st, st, t, mean_x, mean_y, acc);
+            __syncthreads();                               // both warps are done with the slot
+            if (t == 0 && tile + nstages < ntile) issue(tile + nstages);
+            if (++slot == nstages) { slot = 0; parity ^= 1u; }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     auto U = [&](int64_t i) -> float {
         if (kind == 1) return __fsub_rn(HAVE_Y ? ld_elem<YD>(yg, i) : 0.f, mean_y);
@@ -393,10 +407,8 @@ __global__ void __launch_bounds__(SD_THREADS) sdot_pipe_kernel(const void* __res
     };
     __shared__ float sacc[64];
     __shared__ float sh[32];
-    if (t < 64) {
-        for (int64_t i = ntile * SD_TE + t; i < n64; i += 64) acc = __fmaf_rn(U(i), V(i), acc);     // < 64 leftover steps
-        sacc[t] = acc;
-    }
+    for (int64_t i = ntile * SD_TE + t; i < n64; i += 64) acc = __fmaf_rn(U(i), V(i), acc);     // < 64 leftover steps
+    sacc[t] = acc;
     __syncthreads();
     if (t < 32) {
         const int a = t >> 3, l = t & 7;
@@ -535,13 +547,13 @@ extern "C" int qa_tensor_scores_f32(const void* x, int x_dtype, const void* y, i
         // pipelined chains: shared-memory ring of 4096-element stages
         const int yk = y ? y_dtype : 2;
         const int stage_bytes = SD_TE * ((x_dtype == QA_DT_BF16 ? 2 : 4) + (yk == 2 ? 0 : (yk == QA_DT_BF16 ? 2 : 4)));
-        const int nst = std::max(2, std::min(6, 98304 / stage_bytes));
-        const int dyn = SD_COOKED_BYTES + nst * stage_bytes;
+        const int nst = std::max(2, std::min(SD_MAX_STAGES, 196608 / stage_bytes));
+        const int dyn = nst * stage_bytes;
 #define QA_SDOT(XD, YD)                                                                                              \
     do {                                                                                                             \
-        if (cudaFuncSetAttribute(sdot_pipe_kernel<XD, YD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SD_COOKED_BYTES + 98304) != cudaSuccess) \
+        if (cudaFuncSetAttribute(sdot_pipe_kernel<XD, YD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608) != cudaSuccess) \
             return check_launch("qa_tensor_scores_f32 (shared memory attribute)");                                   \
-        sdot_pipe_kernel<XD, YD><<<g, SD_THREADS, dyn, s>>>(x, y, y_stride, n, nnodes, nst, vals, dots);              \
+        sdot_pipe_kernel<XD, YD><<<g, 64, dyn, s>>>(x, y, y_stride, n, nnodes, nst, vals, dots);                      \
     } while (0)
         if (x_dtype == QA_DT_BF16) { if (yk == QA_DT_BF16) QA_SDOT(QA_DT_BF16, QA_DT_BF16); else if (yk == QA_DT_F32) QA_SDOT(QA_DT_BF16, QA_DT_F32); else QA_SDOT(QA_DT_BF16, 2); }
         else { if (yk == QA_DT_BF16) QA_SDOT(QA_DT_F32, QA_DT_BF16); else if (yk == QA_DT_F32) QA_SDOT(QA_DT_F32, QA_DT_F32); else QA_SDOT(QA_DT_F32, 2); }

@@ -259,6 +259,11 @@ __global__ void __launch_bounds__(F32_WARPS * 32, 3) stats_f32_kernel(const void
     accf_zero(a);
     unsigned bad = 0;
     if (col0 < cols) {
+        // fp8 source: a full, 16-byte aligned group is one LDG.128; the next row's is requested before this row is processed
+        const uint8_t* p8 = reinterpret_cast<const uint8_t*>(x) + row0 * ld + col0;
+        const bool full8 = SRC == 1 && col0 + GROUP <= cols && ((reinterpret_cast<uintptr_t>(p8) | (uintptr_t)ld) & 15) == 0;
+        uint4 qn = make_uint4(0u, 0u, 0u, 0u);
+        if (full8 && nrows > 0) qn = __ldg(reinterpret_cast<const uint4*>(p8));
         for (int r = 0; r < nrows; ++r) {
             const int64_t row = row0 + r;
             uint32_t u[GROUP];
@@ -277,11 +282,11 @@ __global__ void __launch_bounds__(F32_WARPS * 32, 3) stats_f32_kernel(const void
                     for (int i = 0; i < GROUP; ++i) u[i] = col0 + i < cols ? p[i] : 0u;
                 }
             } else {
-                const uint8_t* p = reinterpret_cast<const uint8_t*>(x) + row * ld + col0;
+                const uint8_t* p = p8 + (int64_t)r * ld;
                 uint32_t wv[4];
-                if (col0 + GROUP <= cols && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
-                    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
-                    wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+                if (full8) {
+                    wv[0] = qn.x; wv[1] = qn.y; wv[2] = qn.z; wv[3] = qn.w;
+                    if (r + 1 < nrows) qn = __ldg(reinterpret_cast<const uint4*>(p + ld));
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -292,25 +297,32 @@ __global__ void __launch_bounds__(F32_WARPS * 32, 3) stats_f32_kernel(const void
                     }
                 }
                 // one inverse scale per 16-element group when the group lies inside one scale block (block widths are multiples
-                // of 16 in every checkpoint format in use: 128); a group that straddles two blocks looks its scales up per element
+                // of 16 in every checkpoint format in use: 128); a group that straddles two blocks looks its scales up per element.
+                // Columns past the end read as byte 0 = +0.0; a nan code stays a nan (any payload: only arithmetic sees it).
                 const float* srow = src.scale + (row / src.br) * src.scols;
                 const int64_t cb0 = col0 / src.bc, cb1 = min(col0 + GROUP - 1, cols - 1) / src.bc;
                 const float sc0 = srow[cb0];
-                const bool one = cb0 == cb1;
+                if (cb0 == cb1) {
+                    const float2 sc2 = make_float2(sc0, sc0);
 #pragma unroll
-                for (int i = 0; i < GROUP; i += 2) {
-                    const float2 q = e4m3x2_f32(wv[i >> 2] >> (8 * (i & 3)));
-                    const float sca = one ? sc0 : srow[min(col0 + i, cols - 1) / src.bc];
-                    const float scb = one ? sc0 : srow[min(col0 + i + 1, cols - 1) / src.bc];
-                    float va = __fmul_rn(q.x, sca), vb = __fmul_rn(q.y, scb);                      // hf_model_utils.py:209-215
-                    if (va != va) va = __uint_as_float(0x7FC00000u);
-                    if (vb != vb) vb = __uint_as_float(0x7FC00000u);
-                    u[i] = col0 + i < cols ? __float_as_uint(va) : 0u;
-                    u[i + 1] = col0 + i + 1 < cols ? __float_as_uint(vb) : 0u;
+                    for (int i = 0; i < GROUP; i += 2) {
+                        const float2 v = __fmul2_rn(e4m3x2_f32(wv[i >> 2] >> (8 * (i & 3))), sc2);      // hf_model_utils.py:209-215
+                        u[i] = __float_as_uint(v.x);
+                        u[i + 1] = __float_as_uint(v.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < GROUP; i += 2) {
+                        const float2 q = e4m3x2_f32(wv[i >> 2] >> (8 * (i & 3)));
+                        u[i] = __float_as_uint(__fmul_rn(q.x, srow[min(col0 + i, cols - 1) / src.bc]));
+                        u[i + 1] = __float_as_uint(__fmul_rn(q.y, srow[min(col0 + i + 1, cols - 1) / src.bc]));
+                    }
                 }
             }
+            if (inexact) {
 #pragma unroll
-            for (int i = 0; i < GROUP; ++i) bad += (u[i] & 0xFFFFu) != 0u;
+                for (int i = 0; i < GROUP; ++i) bad += (u[i] & 0xFFFFu) != 0u && (u[i] & 0x7FFFFFFFu) <= 0x7F800000u;   // a nan is not counted
+            }
             groupf_fast<EXACT_ABS>(u, a);
         }
     }
