@@ -34,7 +34,7 @@ if str(ROOT) not in sys.path:
 UNIT = "GB/s"
 GREEDY = {"metric": "pcc", "threshold": 0.999, "seed": 123}
 FORMATS5 = ["bf16", "bfp8", "bfp4", "bfp2", "fp0"]
-INFLIGHT = int(os.environ.get("QA_BENCH_INFLIGHT", "8"))          # tensor lists in flight for the device-resident throughput
+INFLIGHT = int(os.environ.get("QA_BENCH_INFLIGHT", "12"))          # tensor lists in flight for the device-resident throughput
 CLUSTER_CAP = int(os.environ["QA_BENCH_CLUSTER_CAP"]) if "QA_BENCH_CLUSTER_CAP" in os.environ else None   # None: the batch's own choice
 TABLE_BYTES_PER_TILE = 22 * 8
 METRICS = {

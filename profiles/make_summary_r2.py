@@ -102,7 +102,8 @@ others = []
 for tag, f in (("cfg1 (none, 5 formats, [1536,7168] x 8 rotating buffers)", "bench_r2_cfg1.json"), ("cfg3 (sweep, 32 thresholds, 8 shapes)", "bench_r2_cfg3.json"),
                ("cfg4 (random, 1000 samples per tensor, 8 shapes)", "bench_r2_cfg4.json"), ("cfg5 N=1 (768 expert tensors)", "bench_r2_cfg5_n1.json"),
                ("cfg5 N=2", "bench_r2_cfg5_n2.json"), ("cfg5 N=4", "bench_r2_cfg5_n4.json"), ("cfg5 N=8", "bench_r2_cfg5_n8.json"),
-               ("cfg2 N=2", "bench_r2_n2.json"), ("cfg2 N=8", "bench_r2_n8.json")):
+               ("cfg2 N=2", "bench_r2_n2.json"), ("cfg2 N=4", "bench_r2_n4.json"), ("cfg2 N=8", "bench_r2_n8.json"),
+               ("cfg2-fp8 (the same list as e4m3fn + 128x128 block scales; GB/s counted at 2 B/elem)", "bench_r2_cfg2_fp8.json")):
     l = line(f)
     if l:
         cb = l.get("cpu_baseline") or {}
@@ -115,20 +116,23 @@ if others:
            "| workload | GB/s of bf16 weights | ms per step | roofline frac (whole step) | e2e GB/s | CPU arm MB/s |", "|---|---:|---:|---:|---:|---|"] + others + [""]
 md += ["## ncu launch list of the bench command (`QA_BENCH_INFLIGHT=2 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 python bench.py --steps 2 --warmup 3 --no-cpu-baseline`;",
        "serialised and cold: compare shares; `profiles/launches_r2.csv`)", ""] + launch_table() + ["",
-       "(`sdot_kernel` dominated this capture: it is the reference-float32 pcc of the plug-in end-to-end leg, 15 calls, taken before that kernel was",
-       "pipelined - 103 ms per o_proj-size call then, 33 ms now, `profiles/r2_scorer_time.txt`; it is not part of a device-resident step.)", "",
-       "## ncu --set full (`profiles/ncu_target.py`: one eager GreedyBatch step, perm cache on; `profiles/r2_raw.csv`)", ""] + pages
+       "(`sdot_pipe_kernel` is the reference-float32 pcc of the plug-in end-to-end leg, 15 calls - 64 sequential FMA chains per dot product by",
+       "definition, 20 ms per o_proj-size call, `profiles/r2_scorer_time.txt`; it is not part of a device-resident step.)", "",
+       "## ncu --set full (`profiles/ncu_target.py`: one eager GreedyBatch step on bf16 tensors, one on the fp8 list, one scorer call; `profiles/r2_raw.csv`)", ""] + pages
 md += ["## Experiments of this round (raw outputs beside this file)", "",
        "* `r2_pipe_ops.txt` - cycles per warp instruction per SM sub-partition for every instruction the tile-stat kernel could use (DESIGN §3.2).",
        "* `r2_stats_variants.txt` - tile-stat kernel alone: 138.1 us (approx-abs mode) / 159.0 us (exact-abs) / 173.4 us with sum|r| moved to the FP64 pipe.",
        "* `r2_phase_overlap.txt` - tile-stat passes, chain group and whole step with 1 / 2 / 4 lists in flight: the two phases ADD (0.2085 + 0.098 = 0.30 ms).",
        "* `r2_step_sweep.txt`, `r2_step_sweep2.txt` - lists in flight x cluster cap.  `r2_chain_regcap.txt` - chain kernel capped at 168 / 128 registers (no gain).",
-       "* `r2_scorer_time.txt` - reference-float32 scorer on 117 M elements: 113 ms -> 33 ms per call (1 or 8 candidates alike: the chains are latency-bound).",
+       "* `r2_chain_regcap2.txt`, `r2_chain_regcap3.txt` - the same cap with 8 / 12 / 16 lists in flight: +4 .. +7 % (shipped: 128 registers, 12 lists).",
+       "* `r2_scorer_time.txt` - reference-float32 scorer on 117 M elements: 113 ms -> 33 ms (cp.async ring) -> 20 ms per call (TMA bulk copies + mbarriers; 1 or 8 candidates alike: the chains are latency-bound).",
+       "* `r2_stats_f32.txt` - tile-stat kernels for inputs that are not bf16-exact: float32 source, fp8 source with fused dequantization, the strict kernel they replace.",
+       "* `r2_chunk_probe.txt` - scoring 32 candidate maps of an o_proj-size tensor in chunks of 8 / 16 / 32 (83 / 45 / 25 ms: one chain latency per call).",
        "* `r2_sass_summary.md` - per-kernel registers, shared memory and opcode mix of the shipped library."]
 (P / "r2_summary.md").write_text("\n".join(md) + "\n")
-for f in ("launches_r2.csv", "r2_raw.csv", "scorer_time.txt"):
+for f in ("launches_r2.csv", "r2_raw.csv", "r2_stats_f32.txt", "r2_scorer_time.txt", "r2b_chunk_probe.txt"):
     if (G / f).exists():
-        shutil.copy(G / f, P / (f if f.startswith("r2_") or f.startswith("launches") else "r2_" + f))
+        shutil.copy(G / f, P / f.replace("r2b_", "r2_"))
 if (G / "bench_r2_final.json").exists():
     shutil.copy(G / "bench_r2_final.json", P / "r2_bench_final.json")
 print("\n".join(md[:20]))

@@ -13,7 +13,8 @@ enum Op {
     F2F64, F2FP_H, F2FP_BF, H2F, I2F, F2I, I2FP_pack, DADD, DFMA,
     SHFL, LDS,
     MIX_FFMA2_LOP3, MIX_HFMA2_LOP3, MIX_FFMA2_HFMA2, MIX_FFMA2_FMNMX, MIX_FFMA2_DFMA, MIX_HFMA2_DFMA, MIX_HFMA2_VIMNMX,
-    MIX_FFMA2_DP4A, MIX_HFMA2_DP4A, MIX_LOP3_DP4A, MIX_FFMA_FFMA2, MIX_HFMA2_F2F64, MIX_3WAY, NOPS
+    MIX_FFMA2_DP4A, MIX_HFMA2_DP4A, MIX_LOP3_DP4A, MIX_FFMA_FFMA2, MIX_HFMA2_F2F64, MIX_3WAY,
+    MIX_FFMA_LOP3, MIX_FADD_FMNMX, MIX_2FFMA_LOP3, MIX_FADD_LOP3_SHL, NOPS
 };
 
 template <int OP>
@@ -121,6 +122,30 @@ __device__ __forceinline__ void step(uint32_t (&r)[8], uint64_t (&q)[8], uint32_
             asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a) : "r"(c0), "r"(c1));
             if ((u & 3) == 0) asm volatile("{.reg .f64 t; cvt.f64.f32 t, %1; add.rn.f64 %0, %0, t;}" : "+l"(b) : "r"(c0));
         }
+        if (OP == MIX_FFMA_LOP3) {      // scalar fp32 + ALU: do these two pipes overlap when the fp32 side is not packed?
+            uint32_t& a2 = reinterpret_cast<uint32_t*>(&b)[0];
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a) : "r"(c0), "r"(c1));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a2) : "r"(c0), "r"(c1));
+        }
+        if (OP == MIX_FADD_FMNMX) {
+            uint32_t& a2 = reinterpret_cast<uint32_t*>(&b)[0];
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(a) : "r"(c0));
+            asm volatile("min.xorsign.abs.f32 %0, %0, %1;" : "+r"(a2) : "r"(c0));
+        }
+        if (OP == MIX_2FFMA_LOP3) {     // two scalar fp32 per ALU instruction
+            uint32_t& a2 = reinterpret_cast<uint32_t*>(&b)[0];
+            uint32_t& a3 = reinterpret_cast<uint32_t*>(&b)[1];
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a) : "r"(c0), "r"(c1));
+            asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a3) : "r"(c0), "r"(c1));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a2) : "r"(c0), "r"(c1));
+        }
+        if (OP == MIX_FADD_LOP3_SHL) {  // one scalar fp32 per two ALU instructions
+            uint32_t& a2 = reinterpret_cast<uint32_t*>(&b)[0];
+            uint32_t& a3 = reinterpret_cast<uint32_t*>(&b)[1];
+            asm volatile("add.rn.f32 %0, %0, %1;" : "+r"(a) : "r"(c0));
+            asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a2) : "r"(c0), "r"(c1));
+            asm volatile("shf.l.wrap.b32 %0, %0, %1, %2;" : "+r"(a3) : "r"(c0), "r"(c1));
+        }
         if (OP == MIX_3WAY) {   // HFMA2 + LOP3 + (every other) DFMA
             asm volatile("fma.rn.f16x2 %0, %0, %1, %2;" : "+r"(a) : "r"(c0), "r"(c1));
             uint32_t& a2 = reinterpret_cast<uint32_t*>(&q[(u + 1) & 7])[1];
@@ -181,5 +206,6 @@ int main() {
     R(F2F64, 2); R(F2FP_H, 1); R(F2FP_BF, 1); R(H2F, 1); R(I2F, 1); R(F2I, 1); R(I2FP_pack, 1); R(DADD, 1); R(DFMA, 1); R(SHFL, 1); R(LDS, 1);
     R(MIX_FFMA2_LOP3, 2); R(MIX_HFMA2_LOP3, 2); R(MIX_FFMA2_HFMA2, 2); R(MIX_FFMA2_FMNMX, 2); R(MIX_FFMA2_DFMA, 2); R(MIX_HFMA2_DFMA, 2);
     R(MIX_HFMA2_VIMNMX, 2); R(MIX_FFMA2_DP4A, 2); R(MIX_HFMA2_DP4A, 2); R(MIX_LOP3_DP4A, 2); R(MIX_FFMA_FFMA2, 2); R(MIX_HFMA2_F2F64, 1); R(MIX_3WAY, 2);
+    R(MIX_FFMA_LOP3, 2); R(MIX_FADD_FMNMX, 2); R(MIX_2FFMA_LOP3, 3); R(MIX_FADD_LOP3_SHL, 3);
     return 0;
 }

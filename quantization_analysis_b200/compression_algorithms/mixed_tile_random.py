@@ -89,7 +89,7 @@ class MixedTileRandomCompression(CompressionAlgorithm):
         import torch
         iters = choices.shape[0]
         per = p.rows * p.cols
-        chunk = max(1, min(iters, (1 << 31) // max(per, 1)))          # <= 4 GiB of bf16 reconstructions at a time
+        chunk = engine.candidate_chunk(per, iters, p.data.device)
         out = np.zeros((iters, 3), dtype=np.float64)
         ys = torch.empty((chunk, per), dtype=torch.bfloat16, device=p.data.device)
         L = engine._lib.lib()

@@ -547,7 +547,11 @@ extern "C" int qa_tensor_scores_f32(const void* x, int x_dtype, const void* y, i
         // pipelined chains: shared-memory ring of 4096-element stages
         const int yk = y ? y_dtype : 2;
         const int stage_bytes = SD_TE * ((x_dtype == QA_DT_BF16 ? 2 : 4) + (yk == 2 ? 0 : (yk == QA_DT_BF16 ? 2 : 4)));
-        const int nst = std::max(2, std::min(SD_MAX_STAGES, 196608 / stage_bytes));
+        // one dot product alone wants a deep ring (latency); a batch larger than the GPU wants many CTAs per SM instead - a lone
+        // warp per sub-partition issues at half rate - so the ring shrinks to what lets 4 - 7 CTAs share an SM's shared memory
+        const int64_t nctas = 2 * (int64_t)nbatch + 1;
+        const int deep = std::max(2, std::min(SD_MAX_STAGES, 196608 / stage_bytes));
+        const int nst = nctas >= 4 * 148 ? 2 : nctas > 148 ? std::min(deep, 3) : deep;
         const int dyn = nst * stage_bytes;
 #define QA_SDOT(XD, YD)                                                                                              \
     do {                                                                                                             \

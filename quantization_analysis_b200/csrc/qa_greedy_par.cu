@@ -1388,13 +1388,18 @@ __global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restr
 // ---------------------------------------------------------------------------------------------
 // the greedy kernel
 // ---------------------------------------------------------------------------------------------
-#ifndef QA_CHAIN_MIN_BLOCKS
-#define QA_CHAIN_MIN_BLOCKS 1
+// The chain kernel is capped at 128 registers (it wants 250): a 256-thread CTA then holds half of an SM's register file and
+// two tile-stat CTAs of the next tensor lists fit beside it.  The cluster kernels issue on ~17 % of the cycles, the tile-stat
+// kernel is pipe-bound, so sharing the SMs pays once enough lists are in flight: cfg2 step 0.286 -> 0.269 ms with 12 lists
+// (profiles/r2_chain_regcap2.txt, r2_chain_regcap3.txt; 96 / 112 registers give the same, 168 nothing), at the price of a
+// 13 % longer chain for a tensor processed alone (0.326 -> 0.369 ms).  -DQA_CHAIN_MAXNREG=0 restores the uncapped kernel.
+#ifndef QA_CHAIN_MAXNREG
+#define QA_CHAIN_MAXNREG 128
 #endif
-#ifdef QA_CHAIN_MAXNREG                    // experiment: cap the chain's registers so tile-stat CTAs can share its SMs
+#if QA_CHAIN_MAXNREG > 0
 #define QA_CHAIN_REGCAP __maxnreg__(QA_CHAIN_MAXNREG)
 #else
-#define QA_CHAIN_REGCAP __launch_bounds__(GT, QA_CHAIN_MIN_BLOCKS)
+#define QA_CHAIN_REGCAP __launch_bounds__(GT, 1)
 #endif
 template <bool PCC, bool INIT_INLINE>      // INIT_INLINE = false: the init phase ran ahead (greedy_init_kernel); its code is left out
 __global__ void QA_CHAIN_REGCAP greedy_par_kernel(const double* __restrict__ table, int nt, double numel, int metric,

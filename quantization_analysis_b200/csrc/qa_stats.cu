@@ -67,10 +67,17 @@ template <> struct Fmt<1> { static constexpr float M = 402653184.f, L = 224.f; }
 template <> struct Fmt<2> { static constexpr float M = 1610612736.f, L = 128.f; };   // bfp2: step 128
 
 // sm_100 packed-float2 arithmetic (FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot)
+#ifdef QA_STATS_SCALAR      // experiment (profiles/r2_stats_variants.txt): scalar FADD / FFMA instead of the packed forms
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+#else
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#endif
 // clamp(y, -L, L) in one instruction: min(|y|, L) with the sign of y (FMNMX.XORSIGN)
 __device__ __forceinline__ float clamp_sym(float y, float L) {
     float r;
@@ -95,7 +102,12 @@ struct GroupAcc {   // in-group float32 partials, two lanes (even / odd element)
 template <int F, bool EXACT_ABS>
 __device__ __forceinline__ void fmt_step(const float2 X, const float2 aX, GroupAcc& g) {
     const float2 Mv = make_float2(Fmt<F>::M, Fmt<F>::M);
+#ifdef QA_STATS_SCALAR_ROUND      // experiment: the rounding as scalar FADDs (they overlap the ALU clamps, the packed forms do not)
+    float2 y = make_float2(__fadd_rn(__fadd_rn(X.x, Fmt<F>::M), -Fmt<F>::M), __fadd_rn(__fadd_rn(X.y, Fmt<F>::M), -Fmt<F>::M));
+    (void)Mv;
+#else
     float2 y = sub2(add2(X, Mv), Mv);                  // round to the format's step, ties to even
+#endif
     y.x = clamp_sym(y.x, Fmt<F>::L);                   // mantissa clamp (no exponent bump)
     y.y = clamp_sym(y.y, Fmt<F>::L);
     const float2 r = sub2(X, y);
@@ -243,8 +255,32 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_k
     TileAcc a;
     acc_zero(a);
     if (col0 < cols) {
+#ifdef QA_STATS_PREFETCH          // experiment: rows in batches of QA_STATS_PREFETCH, the next batch requested before this one is processed
+        constexpr int PB = QA_STATS_PREFETCH, NB = FAST_RPW / PB;
+        uint32_t buf[2][PB][8];
+        auto load_batch = [&](int b, uint32_t (&dst)[PB][8]) {
+#pragma unroll
+            for (int k = 0; k < PB; ++k) {
+                if (b * PB + k < nrows) load_row_group<VEC>(x, row0 + b * PB + k, col0, cols, ld, dst[k]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst[k][i] = 0u;
+                }
+            }
+        };
+        load_batch(0, buf[0]);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b + 1 < NB) load_batch(b + 1, buf[(b + 1) & 1]);
+#pragma unroll
+            for (int k = 0; k < PB; ++k) group_fast<EXACT_ABS>(buf[b & 1][k], a);
+        }
+        int r = nrows;
+        uint32_t cur[1][8];
+#else
         uint32_t cur[FAST_UNROLL][8];
         int r = 0;
+#endif
         for (; r + FAST_UNROLL <= nrows; r += FAST_UNROLL) {
 #pragma unroll
             for (int k = 0; k < FAST_UNROLL; ++k) load_row_group<VEC>(x, row0 + r + k, col0, cols, ld, cur[k]);

@@ -539,6 +539,15 @@ def result_to_numpy(p: Prepared, y_bf16: torch.Tensor) -> np.ndarray:
 _PLANS: dict = {}
 
 
+def candidate_chunk(per: int, wanted: int, device) -> int:
+    """How many bf16 reconstructions of `per` elements to materialise and score per qa_tensor_scores_f32 call: each call costs
+    one chain latency (n / 64 dependent FMAs) whatever the batch, so the batch takes up to half of the free HBM (<= 48 GiB)
+    rather than a fixed few GiB - 180 GB of HBM3e is what makes a 1000-sample run a handful of calls."""
+    free, _total = torch.cuda.mem_get_info(device)
+    budget = min(48 << 30, free // 2)
+    return int(max(1, min(wanted, budget // max(2 * per, 1))))
+
+
 def pairwise_plan_host(n: int) -> np.ndarray:
     """Shape of np.add.reduce's pairwise-summation tree over n contiguous elements (qa_pairwise_plan_build; host only)."""
     L = _lib.lib()

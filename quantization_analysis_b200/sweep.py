@@ -47,7 +47,7 @@ def _score_maps(p: engine.Prepared, maps: torch.Tensor, rows_idx) -> dict[int, n
     """float32 (pcc, mae, atol) of the reconstructions of the given rows of `maps`, batched."""
     L = engine._lib.lib()
     per = p.rows * p.cols
-    chunk = max(1, min(len(rows_idx), (1 << 31) // max(per, 1)))
+    chunk = engine.candidate_chunk(per, len(rows_idx), p.data.device)
     ys = torch.empty((chunk, per), dtype=torch.bfloat16, device=p.data.device)
     out = {}
     for s0 in range(0, len(rows_idx), chunk):
