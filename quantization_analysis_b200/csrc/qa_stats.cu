@@ -352,6 +352,147 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_k
 }
 
 // ------------------------------------------------------------------------------------------
+// FAST, TMA-staged (experiment of round 2, selected with QA_STATS_TMA=1): a persistent CTA walks (tile row, 512-column chunk)
+// items; thread 0 streams 16-row x 512-column half-items (16 bulk copies of 1 KB, one mbarrier per stage) into a two-stage
+// shared-memory ring, each warp pulls its four rows into registers (LDS.128), frees the stage and runs the same group
+// arithmetic.  The row loads leave the warps' scoreboards (12 % of the warp-time of stats_fast_kernel waits on them).
+// ------------------------------------------------------------------------------------------
+constexpr int TS_ROWS = 16, TS_NST = 2, TS_STAGE = TS_ROWS * 512 * 2;
+__device__ __forceinline__ unsigned ts_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ts_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "TS_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra TS_DONE;\n\t"
+        "bra TS_WAIT;\n\t"
+        "TS_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+template <bool EXACT_ABS>
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_tma_kernel(
+    const uint16_t* __restrict__ x, int64_t ld, int64_t tiles_w, int64_t chunks, int64_t item0, int64_t nitems, int64_t ntiles,
+    uint32_t fmt_mask, double* __restrict__ table) {
+    __shared__ __align__(128) unsigned char ring[TS_NST][TS_STAGE];
+    __shared__ __align__(8) unsigned long long full[TS_NST], empty[TS_NST];
+    __shared__ double part[FAST_WARPS - 1][14][32];
+    __shared__ float partmx[FAST_WARPS - 1][3][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s_ = 0; s_ < TS_NST; ++s_) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ts_s32(&full[s_])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ts_s32(&empty[s_])), "r"(FAST_WARPS) : "memory");
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if ((int64_t)blockIdx.x >= nitems) return;
+    const int64_t my_items = (nitems - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t nh = 2 * my_items;                       // half-items of this CTA, in order
+    auto issue = [&](int64_t h) {                          // thread 0: stage h % TS_NST <- half-item h
+        const int64_t item = item0 + blockIdx.x + (h >> 1) * gridDim.x;
+        const int64_t tr = item / chunks, ck = item - tr * chunks;
+        const uint16_t* src = x + (tr * TILE + (h & 1) * TS_ROWS) * ld + ck * 512;
+        const int s_ = (int)(h % TS_NST);
+        const unsigned bar = ts_s32(&full[s_]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)TS_STAGE) : "memory");
+#pragma unroll 4
+        for (int r = 0; r < TS_ROWS; ++r)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             ts_s32(&ring[s_][r * 1024])),
+                         "l"(src + (int64_t)r * ld), "r"(1024u), "r"(bar)
+                         : "memory");
+    };
+    if (threadIdx.x == 0)
+        for (int64_t h = 0; h < nh && h < TS_NST; ++h) issue(h);
+    TileAcc a;
+    acc_zero(a);
+    for (int64_t h = 0; h < nh; ++h) {
+        const int s_ = (int)(h % TS_NST);
+        const unsigned parity = (unsigned)((h / TS_NST) & 1);
+        ts_wait(ts_s32(&full[s_]), parity);
+        uint32_t cur[TS_ROWS / FAST_WARPS][8];
+        const unsigned char* base = &ring[s_][(w * (TS_ROWS / FAST_WARPS)) * 1024 + lane * 32];
+#pragma unroll
+        for (int k = 0; k < TS_ROWS / FAST_WARPS; ++k) {
+            const uint4 lo = *reinterpret_cast<const uint4*>(base + k * 1024), hi = *reinterpret_cast<const uint4*>(base + k * 1024 + 16);
+            cur[k][0] = lo.x; cur[k][1] = lo.y; cur[k][2] = lo.z; cur[k][3] = lo.w;
+            cur[k][4] = hi.x; cur[k][5] = hi.y; cur[k][6] = hi.z; cur[k][7] = hi.w;
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ts_s32(&empty[s_])) : "memory");
+        if (threadIdx.x == 0 && h + TS_NST < nh) {         // every warp has its rows in registers: refill the stage
+            ts_wait(ts_s32(&empty[s_]), parity);
+            issue(h + TS_NST);
+        }
+#pragma unroll
+        for (int k = 0; k < TS_ROWS / FAST_WARPS; ++k) group_fast<EXACT_ABS>(cur[k], a);
+        if (!(h & 1)) continue;
+        // end of an item: the four warps' partial sets are summed in warp order (as in stats_fast_kernel)
+        const int64_t item = item0 + blockIdx.x + (h >> 1) * gridDim.x;
+        const int64_t tr = item / chunks, ck = item - tr * chunks;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) a.sxy[f] += a.sy2[f];
+        if (w > 0) {
+            double (*p)[32] = part[w - 1];
+            p[0][lane] = a.sx; p[1][lane] = a.sx2;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                p[2 + f][lane] = a.sy[f]; p[5 + f][lane] = a.sy2[f]; p[8 + f][lane] = a.sxy[f]; p[11 + f][lane] = a.sab[f];
+                partmx[w - 1][f][lane] = a.amax[f];
+            }
+        }
+        __syncthreads();
+        if (w == 0) {
+#pragma unroll
+            for (int q = 0; q < FAST_WARPS - 1; ++q) {
+                a.sx += part[q][0][lane]; a.sx2 += part[q][1][lane];
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    a.sy[f] += part[q][2 + f][lane]; a.sy2[f] += part[q][5 + f][lane];
+                    a.sxy[f] += part[q][8 + f][lane]; a.sab[f] += part[q][11 + f][lane];
+                    a.amax[f] = fmaxf(a.amax[f], partmx[q][f][lane]);
+                }
+            }
+            a.sx += shfl_xor_d(a.sx, 1);
+            a.sx2 += shfl_xor_d(a.sx2, 1);
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                a.sy[f] += shfl_xor_d(a.sy[f], 1); a.sy2[f] += shfl_xor_d(a.sy2[f], 1);
+                a.sxy[f] += shfl_xor_d(a.sxy[f], 1); a.sab[f] += shfl_xor_d(a.sab[f], 1);
+                a.amax[f] = fmaxf(a.amax[f], __shfl_xor_sync(0xFFFFFFFFu, a.amax[f], 1));
+            }
+            const int64_t tc = ck * 16 + (lane >> 1);
+            if ((lane & 1) == 0 && tc < tiles_w) {
+                const int64_t t = tr * tiles_w + tc;
+                table[QA_STAT_SX * ntiles + t] = a.sx;
+                table[QA_STAT_SX2 * ntiles + t] = a.sx2;
+                if (fmt_mask & 1u) {
+                    table[QA_STAT_FMT(0, 0) * ntiles + t] = a.sx;
+                    table[QA_STAT_FMT(0, 1) * ntiles + t] = a.sx2;
+                    table[QA_STAT_FMT(0, 2) * ntiles + t] = a.sx2;
+                    table[QA_STAT_FMT(0, 3) * ntiles + t] = 0.0;
+                    table[QA_STAT_FMT(0, 4) * ntiles + t] = 0.0;
+                }
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    if (fmt_mask & (2u << f)) {
+                        table[QA_STAT_FMT(f + 1, 0) * ntiles + t] = a.sy[f];
+                        table[QA_STAT_FMT(f + 1, 1) * ntiles + t] = a.sy2[f];
+                        table[QA_STAT_FMT(f + 1, 2) * ntiles + t] = a.sxy[f];
+                        table[QA_STAT_FMT(f + 1, 3) * ntiles + t] = a.sab[f];
+                        table[QA_STAT_FMT(f + 1, 4) * ntiles + t] = (double)a.amax[f];
+                    }
+                }
+            }
+        }
+        __syncthreads();                                   // part[] is free again
+        acc_zero(a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // STRICT
 // ------------------------------------------------------------------------------------------
 constexpr int SP = 33;  // padded smem row pitch
@@ -538,6 +679,13 @@ static int tile_stats_fast(const void* x, int64_t rows, int64_t cols, int64_t ld
     const bool vec = (cols % GROUP == 0) && (ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(x) % 32 == 0);
     const uint16_t* xp = reinterpret_cast<const uint16_t*>(x);
     const bool exact_abs = (mode == QA_STATS_FAST);
+    static const int use_tma = getenv("QA_STATS_TMA") ? atoi(getenv("QA_STATS_TMA")) : 0;
+    if (use_tma && vec && cols % 512 == 0 && rows % TILE == 0) {
+        const unsigned g = (unsigned)std::min<int64_t>(grid, 148 * use_tma);
+        if (exact_abs) stats_tma_kernel<true><<<g, FAST_WARPS * 32, 0, s>>>(xp, ld, tiles_w, chunks, item0, grid, ntiles, fmt_mask, table);
+        else stats_tma_kernel<false><<<g, FAST_WARPS * 32, 0, s>>>(xp, ld, tiles_w, chunks, item0, grid, ntiles, fmt_mask, table);
+        return check_launch("qa_tile_stats(fast, tma)");
+    }
     if (vec && exact_abs) stats_fast_kernel<true, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
     else if (vec) stats_fast_kernel<true, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
     else if (exact_abs) stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
