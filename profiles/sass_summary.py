@@ -35,7 +35,7 @@ for line in sass.splitlines():
         kern[fn][m.group(1)] += 1
 demangle = subprocess.run(["c++filt"], input="\n".join(kern), capture_output=True, text=True).stdout.splitlines()
 INTEREST = ["FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "FMNMX", "FMNMX3", "HFMA2", "DFMA", "DADD", "DMUL", "F2F", "LOP3", "SHF",
-            "PRMT", "IADD3", "IMAD", "LDG", "STG", "LDS", "STS", "LDL", "STL", "SHFL", "BAR", "SYNCS", "ATOMS", "MUFU", "UCGABAR_ARV", "UCGABAR_WAIT"]
+            "PRMT", "IADD3", "IMAD", "LDG", "STG", "LDS", "STS", "LDL", "STL", "SHFL", "BAR", "SYNCS", "UBLKCP", "F2FP", "ATOMS", "MUFU", "UCGABAR_ARV", "UCGABAR_WAIT"]
 out = ["# SASS summary of libqa_b200.so (sm_100a), round 2", "",
        "`python profiles/sass_summary.py` (cuobjdump -sass / -res-usage on the in-tree library; static counts, whole kernel).", "",
        "| kernel | regs | smem B | local B | instrs | " + " | ".join(INTEREST) + " |", "|---|---:|---:|---:|---:|" + "---:|" * len(INTEREST)]
@@ -49,7 +49,8 @@ for (mangled, c), name in zip(kern.items(), demangle):
     out.append(f"| `{short}` | {u[0]} | {u[1]} | {u[2]} | {sum(c.values())} | " + " | ".join(str(base.get(k, 0)) for k in INTEREST) + " |"
                + (f" <!-- {wide} x LDG.256 -->" if wide else ""))
 out += ["", "Markers: packed fp32 (`FFMA2` / `FADD2` / `FMUL2`), `FMNMX3`, `FMNMX.XORSIGN` and 256-bit `LDG.E...256` loads in the streaming kernels;",
-        "`SYNCS` (mbarrier) + distributed-shared-memory stores and `UCGABAR_*` in the cluster kernels; no tensor-core or TMA instructions",
-        "(the path is not a contraction and its loads are already full 32-byte sectors per thread)."]
+        "`SYNCS` (mbarrier) + distributed-shared-memory stores and `UCGABAR_*` in the cluster kernels; TMA bulk copies (`UBLKCP.S.G`, completing on",
+        "`SYNCS.ARRIVE.TRANS64` mbarriers) in `sdot_pipe_kernel` and the opt-in `stats_tma_kernel`; `F2FP` = the hardware e4m3x2 -> f16x2 and f32 -> bf16x2",
+        "conversions of `stats_f32_kernel`; no tensor-core instructions (the path is not a contraction)."]
 (ROOT / "profiles" / "r2_sass_summary.md").write_text("\n".join(out) + "\n")
 print("\n".join(out[:12]))
