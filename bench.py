@@ -411,7 +411,8 @@ def bench_greedy(args, e) -> None:
     shapes = [s for (_n, s, _sd) in items]
 
     def make_batches(perm_cache: bool, n: int):
-        bs = [GreedyBatch(shapes, **GREEDY, device=dev, perm_cache=perm_cache) for _ in range(n)]
+        sg = int(os.environ["QA_BENCH_STATS_GROUP"]) if "QA_BENCH_STATS_GROUP" in os.environ else None      # None: the batch's own choice
+        bs = [GreedyBatch(shapes, **GREEDY, device=dev, perm_cache=perm_cache, stats_group=sg) for _ in range(n)]
         if CLUSTER_CAP is not None and not cfg5:
             for b in bs:
                 b.cluster_cap = CLUSTER_CAP
@@ -608,7 +609,10 @@ def bench_greedy(args, e) -> None:
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    n_stats_launches = sum(3 if (s["ntiles"] >= batch.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8) else 1 for s in batch.slots)
+    if batch.stats_group > 0:        # descriptor-array launches: one tile-stat kernel per group of tensors
+        n_stats_launches = len(batch._groups)
+    else:
+        n_stats_launches = sum(3 if (s["ntiles"] >= batch.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8) else 1 for s in batch.slots)
     ms_stats = time_phase(True, False)
     ms_assign = time_phase(False, True, reps=2)
     ntiles = sum(s["ntiles"] for s in batch.slots)

@@ -103,6 +103,34 @@ int qa_tile_stats_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, i
                        uint32_t fmt_mask, int mode, double* table, int64_t tile_row_begin,
                        int64_t tile_row_end, qa_stream_t stream);
 
+/* Descriptor-array batched variants: one launch for a whole list of tensors - the 768 expert matrices of
+ * a MoE layer (cfg5) are 96 tensors per GPU, each worth a 17 us tile-stat kernel.  The caller owns the descriptor array in
+ * DEVICE memory (it describes resident buffers, so it is built once per tensor list) and fills the two prefix fields:
+ *   item_begin  = sum of qa_tile_stats_items(rows, cols) of the tensors before this one   (tile-stat launch)
+ *   block_begin = sum of ceil(ntiles / 256) of the tensors before this one                (delta-record launch)
+ * x: bf16 [rows][ld]; table: float64 [QA_NSTAT][ntiles]; init: qa_greedy_init_bytes(ntiles) bytes (only read by the delta launch). */
+typedef struct qa_batch_desc {
+    const void* x;
+    double* table;
+    void* init;
+    int64_t rows, cols, ld;
+    int64_t item_begin;
+    int64_t block_begin;
+} qa_batch_desc;
+
+/* host helper: CTAs (tile row x 512-column chunk items) the fast tile-stat pass uses for a [rows, cols] tensor */
+int64_t qa_tile_stats_items(int64_t rows, int64_t cols);
+
+/* qa_tile_stats (fast modes, bf16 input) for n tensors in one launch; total_items = item_begin + items of the last tensor.
+ * Same kernel body per item as qa_tile_stats: the tables are bit-identical to n separate calls. */
+int qa_tile_stats_batch(const qa_batch_desc* descs_dev, int n, int64_t total_items, uint32_t fmt_mask, int mode,
+                        qa_stream_t stream);
+
+/* qa_greedy_init_deltas for n tensors in one launch (the per-transition delta records of mixed_tile_greedy.py:245-254);
+ * total_blocks = block_begin + blocks of the last tensor. */
+int qa_greedy_init_deltas_batch(const qa_batch_desc* descs_dev, int n, int64_t total_blocks, const int32_t* fmt_order, int nfmt,
+                                qa_stream_t stream);
+
 /* The fast tile-stat pass for inputs that are NOT bf16-exact - what the reference's loader produces from real checkpoints
  * (hf_model_utils.py:199-215,271-281: fp8 e4m3fn weights x per-block inverse scales -> float32 with 24-bit significands).
  * Same table as qa_tile_stats, all four formats (bf16 is a real quantization for these inputs), same lane-owns-a-group

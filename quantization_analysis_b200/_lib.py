@@ -25,12 +25,18 @@ EXPORTS = [
     "qa_threshold_assign", "qa_random_samples", "qa_apply_assignment", "qa_assignment_sums", "qa_assignment_sums_batch",
     "qa_f32_to_bf16_checked", "qa_scalar_proxy", "qa_fp8_block_dequant", "qa_greedy_par_work_bytes", "qa_greedy_assign_par", "qa_numpy_permutation_par", "qa_collective_bench", "qa_debug_times", "qa_greedy_cluster_cap", "qa_greedy_prefetch", "qa_greedy_assign_par_pre", "qa_greedy_assign_passes", "qa_greedy_init", "qa_greedy_init_sums", "qa_greedy_init_sums_range", "qa_greedy_init_deltas", "qa_tile_stats_rows", "qa_greedy_init_bytes", "qa_perm_resolve", "qa_perm_resolve_chain", "qa_perm_apply", "qa_perm_apply_work_bytes", "qa_pair_sums", "qa_pair_sums_work_bytes",
     "qa_pairwise_plan_words", "qa_pairwise_plan_build", "qa_tensor_scores_work_bytes", "qa_tensor_scores_f32",
-    "qa_tile_stats_f32", "qa_tile_stats_fp8",
+    "qa_tile_stats_f32", "qa_tile_stats_fp8", "qa_tile_stats_items", "qa_tile_stats_batch", "qa_greedy_init_deltas_batch",
 ]
 
 
 class QaError(RuntimeError):
     pass
+
+
+class BatchDesc(C.Structure):
+    """qa_batch_desc of include/qa_b200.h (one tensor of a descriptor-array launch)."""
+    _fields_ = [("x", C.c_void_p), ("table", C.c_void_p), ("init", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64),
+                ("ld", C.c_int64), ("item_begin", C.c_int64), ("block_begin", C.c_int64)]
 
 
 def _sources_newer() -> bool:
@@ -101,6 +107,10 @@ def lib():
     L.qa_tile_stats_rows.argtypes = [vp, i32, i64, i64, i64, u32, i32, vp, i64, i64, vp]
     L.qa_tile_stats_f32.argtypes = [vp, i64, i64, i64, u32, i32, vp, i64, i64, vp]
     L.qa_tile_stats_fp8.argtypes = [vp, vp, i64, i64, i64, i64, i64, u32, i32, vp, i64, i64, vp, vp]
+    L.qa_tile_stats_items.argtypes = [i64, i64]
+    L.qa_tile_stats_items.restype = i64
+    L.qa_tile_stats_batch.argtypes = [vp, i32, i64, u32, i32, vp]
+    L.qa_greedy_init_deltas_batch.argtypes = [vp, i32, i64, C.POINTER(C.c_int32), i32, vp]
     L.qa_threshold_assign.argtypes = [vp, i64, C.POINTER(C.c_int32), i32, i32, vp, i32, vp, vp, vp]
     L.qa_random_samples.argtypes = [vp, i64, f64, C.POINTER(C.c_int32), i32, i32, vp, vp, i32, vp, vp, vp]
     L.qa_apply_assignment.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp]
@@ -118,7 +128,7 @@ def lib():
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("qa_last_error", "qa_greedy_work_bytes", "qa_greedy_par_work_bytes", "qa_greedy_init_bytes", "qa_perm_apply_work_bytes", "qa_version",
-                        "qa_pair_sums_work_bytes", "qa_pairwise_plan_words", "qa_tensor_scores_work_bytes"):
+                        "qa_pair_sums_work_bytes", "qa_pairwise_plan_words", "qa_tensor_scores_work_bytes", "qa_tile_stats_items"):
             fn.restype = i32
     _lib = L
     return L

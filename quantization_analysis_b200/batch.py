@@ -68,12 +68,21 @@ class GreedyBatch:
 
     def __init__(self, shapes, metric: str = "pcc", threshold: float = 0.999, seed: int = 123,
                  tile_formats=MIXED, n_streams: int | None = None, device=None, perm_cache: bool = False,
-                 source: str = "bf16", scale_block=(128, 128)):
+                 source: str = "bf16", scale_block=(128, 128), stats_group: int | None = None):
         """source="bf16": resident bf16 tensors (the default).  source="fp8": e4m3fn bytes + a float32 inverse-scale grid per
         tensor, one scale per `scale_block` elements as checkpoints store them (hf_model_utils.py:199-215); the tile-stat pass
         dequantizes on the fly (qa_tile_stats_fp8) and everything behind the table is unchanged."""
         if source not in ("bf16", "fp8"):
             raise ValueError("source must be 'bf16' or 'fp8'")
+        # stats_group = G > 0: the device-resident pass (run / run_graph) issues the tile-stat pass and the delta records of G
+        # tensors at a time as ONE descriptor-array launch each (qa_tile_stats_batch, qa_greedy_init_deltas_batch) instead of
+        # one launch per tensor.  Off by default: on cfg5 (768 expert tensors in one CUDA graph) one launch per tensor lets
+        # every tensor's chain start behind its own 17 us tile-stat kernel, a group's chains wait for the whole group
+        # (15.6 ms per step ungrouped, 17.2 / 20.8 / 21.9 ms with G = 8 / 32 / 96; profiles/r2_cfg5_group_sweep.txt).  The
+        # entry points are for callers without a graph, where 3 000 launches per step cost host time.
+        if stats_group is None:
+            stats_group = 0
+        self.stats_group = int(stats_group) if source == "bf16" else 0
         self.source, self.scale_block = source, (int(scale_block[0]), int(scale_block[1]))
         self.device = device or engine._require_cuda()
         self.perm_cache = bool(perm_cache)
@@ -142,6 +151,18 @@ class GreedyBatch:
             for s_ in self.slots:
                 hit = cached_permutations(self.device, self.seed, s_["ntiles"], len(self.tile_formats))
                 s_["pre_order"], s_["rngs"] = hit["pre_order"], hit["rngs"]
+        self._groups = []
+        if self.stats_group > 0:
+            run_order = sorted(range(len(self.slots)), key=lambda i: -self.slots[i]["ntiles"])
+            for g0 in range(0, len(run_order), self.stats_group):
+                members = run_order[g0:g0 + self.stats_group]
+                descs, n, items, blocks = engine.batch_descriptors(
+                    [(self.slots[i]["x"].data_ptr(), self.slots[i]["table"].data_ptr(), self.slots[i]["init"].data_ptr(),
+                      self.slots[i]["rows"], self.slots[i]["cols"]) for i in members], self.device)
+                grp = {"members": members, "descs": descs, "n": n, "items": items, "blocks": blocks, "ev": torch.cuda.Event()}
+                self._groups.append(grp)
+                for i in members:
+                    self.slots[i]["group"] = grp
         self._rng0 = rng0
         self._graphs = {}
         self.trace = None            # set to {} to record per-tensor stage events during eager run() (see timeline())
@@ -162,9 +183,12 @@ class GreedyBatch:
                     n -= 1                       # resident permutations: the chain is one launch
                 if lead and not self.perm_cache:
                     n += (2 + 2 * 7) if len(self.tile_formats) >= 3 else (1 + 7)
-            if metric != "atol" and s["ntiles"] >= self.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8:
+            if self.stats_group > 0:
+                n -= 1 if metric == "atol" else 2            # tile-stat pass and delta records come from the group launches
+            elif metric != "atol" and s["ntiles"] >= self.PIPELINE_MIN_TILES and -(-s["rows"] // 32) >= 8:
                 n += 4
             self.launches_per_step += n
+        self.launches_per_step += len(self._groups) * (1 if metric == "atol" else 2)
 
     # ---- data movement -------------------------------------------------------------------
     def load_device(self, tensors) -> None:
@@ -204,7 +228,9 @@ class GreedyBatch:
                                        slot["table"].data_ptr(), lo, hi, sp), "qa_tile_stats_rows")
 
     # ---- compute -------------------------------------------------------------------------
-    def _enqueue(self, slot, stream, stats: bool = True, assign: bool = True, side=None) -> None:
+    def _enqueue(self, slot, stream, stats: bool = True, assign: bool = True, side=None, pre_event=None) -> None:
+        """pre_event: the tensor's table (and delta records) come from a group launch that signals this event; only the
+        per-tensor cluster kernels are enqueued here."""
         L = _lib.lib()
         sp = stream.cuda_stream
         pre = assign and self.prefetch and side is not None
@@ -296,6 +322,9 @@ class GreedyBatch:
                 self._stats(slot, mode, 0, tiles_h, ss.cuda_stream)
             stream.wait_stream(ss)
             mark("stats")
+        elif pre_event is not None:
+            stream.wait_event(pre_event)
+            mark("stats")
         if assign:
             if not pre or (lead and len(self.tile_formats) < 3):
                 slot["rng"].copy_(self._rng0, non_blocking=True)      # every tensor restarts the seeded stream
@@ -314,6 +343,8 @@ class GreedyBatch:
                     tiles_w = -(-slot["cols"] // 32)
                     check(L.qa_greedy_init_sums_range(*iargs, split * tiles_w, slot["ntiles"], sp), "qa_greedy_init_sums_range")
                     stream.wait_stream(ss)
+                elif pre_event is not None:
+                    check(L.qa_greedy_init_sums_range(*iargs, 0, slot["ntiles"], sp), "qa_greedy_init_sums_range")
                 else:
                     check(L.qa_greedy_init(*iargs, sp), "qa_greedy_init")
                 mark("init")
@@ -355,11 +386,25 @@ class GreedyBatch:
             _lib.lib().qa_greedy_cluster_cap(prev_cap)
 
     def _run_ordered(self, cur, order, stats, assign) -> None:
+        grouped = stats and self.stats_group > 0
+        if grouped:
+            L = _lib.lib()
+            mode = STATS_FAST if self.metric == "mae" else STATS_FAST_APPROX_ABS
+            for gi, grp in enumerate(self._groups):
+                ss = self.stats_streams[gi % len(self.stats_streams)]
+                ss.wait_stream(cur)
+                check(L.qa_tile_stats_batch(grp["descs"].data_ptr(), grp["n"], grp["items"], 0xF, mode, ss.cuda_stream), "qa_tile_stats_batch")
+                if assign and self.metric != "atol":
+                    check(L.qa_greedy_init_deltas_batch(grp["descs"].data_ptr(), grp["n"], grp["blocks"], self._order, len(self.tile_formats),
+                                                        ss.cuda_stream), "qa_greedy_init_deltas_batch")
+                grp["ev"].record(ss)
         for k, i in enumerate(order):
             st = self.streams[k % len(self.streams)]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                self._enqueue(self.slots[i], st, stats, assign, side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]))
+                self._enqueue(self.slots[i], st, stats and not grouped, assign,
+                              side=(self.side_streams[k % len(self.side_streams)], self.side2_streams[k % len(self.side2_streams)]),
+                              pre_event=self.slots[i]["group"]["ev"] if grouped else None)
         for st in self.streams:
             cur.wait_stream(st)
 

@@ -1385,6 +1385,34 @@ __global__ void __launch_bounds__(256) greedy_delta_kernel(const double* __restr
     }
 }
 
+// the same for a descriptor array of tensors: block b finds its tensor by bisection over the block prefix
+__global__ void __launch_bounds__(256) greedy_delta_batch_kernel(const qa_batch_desc* __restrict__ descs, int n, ParOrder ord, int64_t hdr_bytes) {
+    const int64_t b = blockIdx.x;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&descs[mid].block_begin) <= b) lo = mid; else hi = mid - 1;
+    }
+    const qa_batch_desc d = descs[lo];
+    const int nt = (int)(cdiv(d.rows, TILE) * cdiv(d.cols, TILE));
+    const int t = (int)(b - d.block_begin) * 256 + threadIdx.x;
+    if (t >= nt) return;
+    const double* table = d.table;
+    double* delta = reinterpret_cast<double*>(reinterpret_cast<char*>(d.init) + hdr_bytes);
+    double v[QA_NFMT][4];
+#pragma unroll
+    for (int f = 0; f < QA_NFMT; ++f)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[f][q] = f < ord.n ? table[(size_t)QA_STAT_FMT(ord.fmt[f], q) * nt + t] : 0.0;
+#pragma unroll
+    for (int tr = 0; tr + 1 < QA_NFMT; ++tr) {
+        if (tr + 1 >= ord.n) break;
+        double2* dst = reinterpret_cast<double2*>(delta + ((size_t)tr * nt + t) * 4);
+        dst[0] = make_double2(__dsub_rn(v[tr + 1][0], v[tr][0]), __dsub_rn(v[tr + 1][1], v[tr][1]));
+        dst[1] = make_double2(__dsub_rn(v[tr + 1][2], v[tr][2]), __dsub_rn(v[tr + 1][3], v[tr][3]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the greedy kernel
 // ---------------------------------------------------------------------------------------------
@@ -2064,6 +2092,15 @@ extern "C" int qa_greedy_init_sums_range(const double* table, int64_t ntiles, in
 extern "C" int qa_greedy_init_deltas(const double* table, int64_t ntiles, int metric, const int32_t* fmt_order, int nfmt, void* init,
                                      qa_stream_t stream) {
     return greedy_init_launch(table, ntiles, metric, fmt_order, nfmt, init, false, true, false, stream, "qa_greedy_init_deltas");
+}
+
+extern "C" int qa_greedy_init_deltas_batch(const qa_batch_desc* descs_dev, int n, int64_t total_blocks, const int32_t* fmt_order, int nfmt,
+                                           qa_stream_t stream) {
+    if (!descs_dev || n <= 0 || total_blocks <= 0 || total_blocks > 0x7FFFFFFF) { set_error("qa_greedy_init_deltas_batch: bad args"); return 1; }
+    ParOrder ord;
+    if (fill_order(fmt_order, nfmt, ord, "qa_greedy_init_deltas_batch")) return 1;
+    greedy_delta_batch_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, n, ord, al(8 * HDR_DOUBLES));
+    return check_launch("qa_greedy_init_deltas_batch");
 }
 
 extern "C" int qa_greedy_assign_passes(const double* table, int64_t ntiles, double numel, int metric, double threshold,

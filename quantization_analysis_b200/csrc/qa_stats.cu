@@ -240,13 +240,11 @@ constexpr int FAST_UNROLL = FAST_UNROLL_N;
 // result is deterministic, and exact whenever the float64 sums are representable).  Small items
 // keep the last wave short: o_proj is 7168 CTAs = 12 waves of 592 instead of 3.03 waves of big ones.
 template <bool VEC, bool EXACT_ABS>
-__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_kernel(
-    const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
-    int64_t chunks, int64_t item0, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
-    __shared__ double part[FAST_WARPS - 1][14][32];
-    __shared__ float partmx[FAST_WARPS - 1][3][32];
+__device__ __forceinline__ void stats_fast_item(double (&part)[FAST_WARPS - 1][14][32], float (&partmx)[FAST_WARPS - 1][3][32],
+                                                const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
+                                                int64_t chunks, int64_t item, int64_t ntiles, uint32_t fmt_mask,
+                                                double* __restrict__ table) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t item = blockIdx.x + item0;          // item0 > 0: a launch that covers a range of tile rows
     const int64_t tr = item / chunks;
     const int64_t ck = item - tr * chunks;
     const int64_t col0 = ck * 512 + (int64_t)lane * GROUP;
@@ -349,6 +347,36 @@ __global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_k
             }
         }
     }
+}
+
+template <bool VEC, bool EXACT_ABS>
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_kernel(
+    const uint16_t* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, int64_t tiles_w,
+    int64_t chunks, int64_t item0, int64_t ntiles, uint32_t fmt_mask, double* __restrict__ table) {
+    __shared__ double part[FAST_WARPS - 1][14][32];
+    __shared__ float partmx[FAST_WARPS - 1][3][32];
+    // item0 > 0: a launch that covers a range of tile rows
+    stats_fast_item<VEC, EXACT_ABS>(part, partmx, x, rows, cols, ld, tiles_w, chunks, blockIdx.x + item0, ntiles, fmt_mask, table);
+}
+
+// Descriptor-array batch: CTA b finds its tensor by bisection over the item prefix and runs the same item body.
+template <bool EXACT_ABS>
+__global__ void __launch_bounds__(FAST_WARPS * 32, FAST_MIN_BLOCKS) stats_fast_batch_kernel(const qa_batch_desc* __restrict__ descs, int n,
+                                                                                            uint32_t fmt_mask) {
+    __shared__ double part[FAST_WARPS - 1][14][32];
+    __shared__ float partmx[FAST_WARPS - 1][3][32];
+    const int64_t b = blockIdx.x;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&descs[mid].item_begin) <= b) lo = mid; else hi = mid - 1;
+    }
+    const qa_batch_desc d = descs[lo];
+    const int64_t tiles_h = cdiv(d.rows, TILE), tiles_w = cdiv(d.cols, TILE), chunks = cdiv(d.cols, 512);
+    const uint16_t* x = reinterpret_cast<const uint16_t*>(d.x);
+    const bool vec = (d.cols % GROUP == 0) && (d.ld % GROUP == 0) && (reinterpret_cast<uintptr_t>(d.x) % 32 == 0);
+    if (vec) stats_fast_item<true, EXACT_ABS>(part, partmx, x, d.rows, d.cols, d.ld, tiles_w, chunks, b - d.item_begin, tiles_h * tiles_w, fmt_mask, d.table);
+    else stats_fast_item<false, EXACT_ABS>(part, partmx, x, d.rows, d.cols, d.ld, tiles_w, chunks, b - d.item_begin, tiles_h * tiles_w, fmt_mask, d.table);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -691,6 +719,21 @@ static int tile_stats_fast(const void* x, int64_t rows, int64_t cols, int64_t ld
     else if (exact_abs) stats_fast_kernel<false, true><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
     else stats_fast_kernel<false, false><<<(unsigned)grid, FAST_WARPS * 32, 0, s>>>(xp, rows, cols, ld, tiles_w, chunks, item0, ntiles, fmt_mask, table);
     return check_launch("qa_tile_stats(fast)");
+}
+
+extern "C" int64_t qa_tile_stats_items(int64_t rows, int64_t cols) {
+    if (rows <= 0 || cols <= 0) return 0;
+    return cdiv(rows, TILE) * cdiv(cols, 512);
+}
+
+extern "C" int qa_tile_stats_batch(const qa_batch_desc* descs_dev, int n, int64_t total_items, uint32_t fmt_mask, int mode,
+                                   qa_stream_t stream) {
+    if (!descs_dev || n <= 0 || total_items <= 0 || total_items > 0x7FFFFFFF) { set_error("qa_tile_stats_batch: bad args"); return 1; }
+    if (mode != QA_STATS_FAST && mode != QA_STATS_FAST_APPROX_ABS) { set_error("qa_tile_stats_batch: fast modes only"); return 1; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mode == QA_STATS_FAST) stats_fast_batch_kernel<true><<<(unsigned)total_items, FAST_WARPS * 32, 0, s>>>(descs_dev, n, fmt_mask & 0xFu);
+    else stats_fast_batch_kernel<false><<<(unsigned)total_items, FAST_WARPS * 32, 0, s>>>(descs_dev, n, fmt_mask & 0xFu);
+    return check_launch("qa_tile_stats_batch");
 }
 
 extern "C" int qa_tile_stats_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ld, uint32_t fmt_mask, int mode,

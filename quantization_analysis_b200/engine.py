@@ -221,6 +221,28 @@ def tile_stats_fp8(w_fp8: torch.Tensor, scale_inv: torch.Tensor, formats=MIXED_F
     return table, cnt
 
 
+def batch_descriptors(entries, device):
+    """Device-resident qa_batch_desc array for a list of resident bf16 tensors.
+    entries: (x data_ptr, table data_ptr, init data_ptr or 0, rows, cols) per tensor.
+    -> (uint8 device tensor holding the array, n, total tile-stat items, total 256-tile delta blocks)."""
+    L = _lib.lib()
+    arr = (_lib.BatchDesc * len(entries))()
+    items = blocks = 0
+    for d, (xp, tp, ip, rows, cols) in zip(arr, entries):
+        d.x, d.table, d.init, d.rows, d.cols, d.ld = xp, tp, ip or None, rows, cols, cols
+        d.item_begin, d.block_begin = items, blocks
+        items += L.qa_tile_stats_items(rows, cols)
+        blocks += -(-((-(-rows // TILE)) * (-(-cols // TILE))) // 256)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device), len(entries), int(items), int(blocks)
+
+
+def tile_stats_batch(descs: torch.Tensor, n: int, total_items: int, formats=MIXED_FORMATS, exact_abs: bool = True) -> None:
+    """qa_tile_stats (fast) for a whole descriptor array in one launch; the tables named by the descriptors are filled."""
+    mode = STATS_FAST if exact_abs else STATS_FAST_APPROX_ABS
+    check(_lib.lib().qa_tile_stats_batch(_ptr(descs), n, total_items, fmt_mask(formats), mode, _stream()), "qa_tile_stats_batch")
+
+
 def fp8_block_dequant(w_fp8: torch.Tensor, scale_inv: torch.Tensor, want_bf16: bool = True):
     """fp8 e4m3fn [rows, cols] (uint8 or float8_e4m3fn storage) * scale_inv blocks -> (float32 tensor, bf16 tensor or None,
     number of products that are not bf16-exact).  hf_model_utils.py:199-215 on the device."""

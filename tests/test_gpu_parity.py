@@ -859,3 +859,43 @@ def test_fp8_fused_tile_stats_and_greedy(qa):
     pinned = [(t.pin_memory(), s_.pin_memory()) for t, s_ in srcs]
     res = b.run_from_host(pinned)
     assert np.array_equal(res[1]["assignment"], a2) and res[0]["counts"] == counts
+
+
+def test_descriptor_array_batch_equals_per_tensor_calls(qa):
+    """qa_tile_stats_batch / qa_greedy_init_deltas_batch (one launch for a list of tensors) fill the same bits as
+    one call per tensor - incl. a ragged tensor that takes the scalar-load path - and GreedyBatch with grouped launches gives
+    the maps of the per-tensor schedule."""
+    from quantization_analysis_b200 import _lib, synthetic
+    from quantization_analysis_b200.batch import GreedyBatch
+    eng = qa["engine"]
+    L = _lib.lib()
+    shapes = [(256, 1024), (96, 320), (45, 77), (512, 512), (64, 2048)]
+    xs = [synthetic.randn_bf16_cpu(s, 40 + i).cuda() for i, s in enumerate(shapes)]
+    preps = [eng.prepare_tiles(x) for x in xs]
+    want = [eng.tile_stats(p, G.MIXED, exact_abs=False) for p in preps]
+    tables = [torch.zeros_like(t) for t in want]
+    inits = [torch.zeros(L.qa_greedy_init_bytes(p.ntiles), dtype=torch.uint8, device="cuda") for p in preps]
+    descs, n, items, blocks = eng.batch_descriptors(
+        [(p.data.data_ptr(), t.data_ptr(), i_.data_ptr(), p.rows, p.cols) for p, t, i_ in zip(preps, tables, inits)], torch.device("cuda"))
+    assert items == sum(L.qa_tile_stats_items(p.rows, p.cols) for p in preps)
+    eng.tile_stats_batch(descs, n, items, G.MIXED, exact_abs=False)
+    for t, w in zip(tables, want):
+        assert torch.equal(t, w)
+    order = _lib.int32_array([0, 1, 2, 3])
+    sp = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.qa_greedy_init_deltas_batch(descs.data_ptr(), n, blocks, order, 4, sp), "qa_greedy_init_deltas_batch")
+    for p, t, i_ in zip(preps, want, inits):
+        ref = torch.zeros_like(i_)
+        _lib.check(L.qa_greedy_init_deltas(t.data_ptr(), p.ntiles, 0, order, 4, ref.data_ptr(), sp), "qa_greedy_init_deltas")
+        assert torch.equal(i_[256:], ref[256:])            # the delta records (behind the 256-byte header the sums kernel writes)
+    vshapes = [s for s in shapes if s != (45, 77)]
+    vx = [x for x, s in zip(xs, shapes) if s != (45, 77)]
+    for metric, thr in (("pcc", 0.999), ("mae", 3e-4), ("atol", 2e-3)):
+        a = GreedyBatch(vshapes, metric=metric, threshold=thr, seed=7, stats_group=0)
+        b = GreedyBatch(vshapes, metric=metric, threshold=thr, seed=7, stats_group=3)
+        for bb in (a, b):
+            bb.load_device(vx)
+            bb.run_graph()
+        for ra, rb in zip(a.collect(), b.collect()):
+            assert np.array_equal(ra["assignment"], rb["assignment"]) and ra["counts"] == rb["counts"], metric
+            assert ra["metrics"] == rb["metrics"], metric
