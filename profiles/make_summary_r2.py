@@ -127,6 +127,9 @@ md += ["## Experiments of this round (raw outputs beside this file)", "",
        "* `r2_chain_regcap2.txt`, `r2_chain_regcap3.txt` - the same cap with 8 / 12 / 16 lists in flight: +4 .. +7 % (shipped: 128 registers, 12 lists).",
        "* `r2_scorer_time.txt` - reference-float32 scorer on 117 M elements: 113 ms -> 33 ms (cp.async ring) -> 20 ms per call (TMA bulk copies + mbarriers; 1 or 8 candidates alike: the chains are latency-bound).",
        "* `r2_stats_f32.txt` - tile-stat kernels for inputs that are not bf16-exact: float32 source, fp8 source with fused dequantization, the strict kernel they replace.",
+       "* `r2_stats_variants2.txt`, `r2_stats_scalar.txt`, `r2_stats_tma.txt` - tile-stat kernel with scalar fp32 / scalar rounding / row prefetch / TMA-staged persistent CTAs: 148 - 171 us against 138 us shipped; `r2_stall_samples.md` - per-instruction stall samples of the shipped kernel and of the cluster kernels.",
+       "* `r2_cfg5_group_sweep.txt` - cfg5 with descriptor-array launches of G tensors (qa_tile_stats_batch): slower than one launch per tensor inside a CUDA graph (15.6 ms vs 17.2 - 21.9 ms).",
+       "* `r2_pytest_1gpu.txt`, `r2_pytest_2gpu.txt` - the `-m gpu` suite on one and on two GPUs (the NCCL striped test runs on two).",
        "* `r2_chunk_probe.txt` - scoring 32 candidate maps of an o_proj-size tensor in chunks of 8 / 16 / 32 (83 / 45 / 25 ms: one chain latency per call).",
        "* `r2_sass_summary.md` - per-kernel registers, shared memory and opcode mix of the shipped library."]
 (P / "r2_summary.md").write_text("\n".join(md) + "\n")
