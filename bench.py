@@ -35,6 +35,7 @@ UNIT = "GB/s"
 GREEDY = {"metric": "pcc", "threshold": 0.999, "seed": 123}
 FORMATS5 = ["bf16", "bfp8", "bfp4", "bfp2", "fp0"]
 INFLIGHT = int(os.environ.get("QA_BENCH_INFLIGHT", "12"))          # tensor lists in flight for the device-resident throughput
+CFG5_INFLIGHT = int(os.environ.get("QA_BENCH_CFG5_INFLIGHT", "3"))      # cfg5: copies of the rank's shard in flight (22.5 GB / world each)
 CLUSTER_CAP = int(os.environ["QA_BENCH_CLUSTER_CAP"]) if "QA_BENCH_CLUSTER_CAP" in os.environ else None   # None: the batch's own choice
 TABLE_BYTES_PER_TILE = 22 * 8
 METRICS = {
@@ -273,7 +274,11 @@ def config_dict(cfg: str, n_gpus: int) -> dict:
          "cfg4": "configs[3]: mixed-tile-random, 1000 samples per tensor (pcc>=0.99), same 8 shapes, every sample scored in the reference's float32",
          "cfg5": "configs[4]: mixed-tile-greedy pcc>=0.999 seed 123 over one MoE layer (256 experts x gate/up [2048,7168] + down "
                  "[7168,2048] = 768 tensors, 22.5 GB), bin-packed over the ranks by partition_tensors"}[cfg]
-    return {"workload": w, "parallelism": f"tensor-list over {n_gpus} rank(s)", "l2": "inputs_larger_than_l2"}
+    out = {"workload": w, "parallelism": f"tensor-list over {n_gpus} rank(s)", "l2": "inputs_larger_than_l2"}
+    if cfg == "cfg5":
+        out["inflight"] = (f"{CFG5_INFLIGHT} copies of the rank's shard in flight (each with its own buffers): the chains of a step's last tensors "
+                           "run under the next step's tile-stat passes; step_latency_ms is one step alone")
+    return out
 
 
 def maps_vs_reference_goldens(items, *result_sets):
@@ -403,7 +408,7 @@ def bench_greedy(args, e) -> None:
         items = [(all_items[i][0], all_items[i][1], 5000 + i) for i in mine]
         uniq = [synthetic.randn_bf16_cpu(s, 50 + j).pin_memory() for j, s in enumerate(synthetic.EXPERT_SHAPES.values())]
         host = [uniq[list(synthetic.EXPERT_SHAPES.values()).index(tuple(s))] for (_n, s, _sd) in items]   # 3 distinct host tensors
-        inflight = 1
+        inflight = CFG5_INFLIGHT
     else:
         items = workload(rank)
         host = [synthetic.randn_bf16_cpu(shape, seed).pin_memory() for (_n, shape, seed) in items]
