@@ -1,0 +1,8 @@
+# lists in flight x cluster cap with the 128-register chain kernel (cfg2 step, perm cache)
+for pt in "12 0" "12 8" "16 8" "12 4" "16 4" "24 4"; do
+  set -- $pt
+  QA_BENCH_INFLIGHT=$1 QA_BENCH_CLUSTER_CAP=$2 python bench.py --steps 48 --warmup 4 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+b=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('inflight $1 cap $2: value %.0f GB/s  ms/step %.4f  uncached %.0f  latency %.3f ms  maps ok %s' % (b['value'], b['ms_per_step'], b['value_uncached'], b['step_latency_ms'], b['result_check']['maps_equal_reference']))"
+done
