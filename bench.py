@@ -36,7 +36,10 @@ GREEDY = {"metric": "pcc", "threshold": 0.999, "seed": 123}
 FORMATS5 = ["bf16", "bfp8", "bfp4", "bfp2", "fp0"]
 INFLIGHT = int(os.environ.get("QA_BENCH_INFLIGHT", "12"))          # tensor lists in flight for the device-resident throughput
 CFG5_INFLIGHT = int(os.environ.get("QA_BENCH_CFG5_INFLIGHT", "3"))      # cfg5: copies of the rank's shard in flight (22.5 GB / world each)
-CLUSTER_CAP = int(os.environ["QA_BENCH_CLUSTER_CAP"]) if "QA_BENCH_CLUSTER_CAP" in os.environ else None   # None: the batch's own choice
+# cfg2: CTAs per chain cluster (0: automatic, up to 16).  Smaller clusters hold fewer SMs per tensor: the throughput schedule
+# (profiles/r2_step_sweep3.txt: 12 lists x 4-CTA clusters 0.250 ms per step at 1.19 ms for a step alone; automatic clusters 0.265 ms
+# at 0.52 ms).  The line reports the latter as `latency_schedule`.
+CLUSTER_CAP = int(os.environ.get("QA_BENCH_CLUSTER_CAP", "4"))
 TABLE_BYTES_PER_TILE = 22 * 8
 METRICS = {
     "cfg1": "bf16 weight GB/s quantized+scored (none: bf16/bfp8/bfp4/bfp2/fp0 on q_a_proj [1536,7168])",
@@ -266,6 +269,8 @@ def config_dict(cfg: str, n_gpus: int) -> dict:
                           "eager stream launches for e2e",
                 "inflight": f"{INFLIGHT} tensor lists in flight, each with its own buffers (the tile-stat passes of later steps overlap the greedy chains of earlier ones); "
                             "step_latency_ms is one step alone",
+                "clusters": (f"chain clusters capped at {CLUSTER_CAP} CTAs per tensor (throughput schedule: a tensor's chain holds fewer SMs for longer); "
+                             "latency_schedule = one step alone with automatic cluster sizes") if CLUSTER_CAP else "automatic cluster sizes (up to 16 CTAs per tensor)",
                 "perm_cache": "value: the NumPy permutations of each (seed, tile count) are drawn once per process and reused by every "
                               "step - what a multi-layer model run does, every layer repeating the same shapes under one seed; "
                               "value_uncached redraws them on the device in every step"}
@@ -415,12 +420,12 @@ def bench_greedy(args, e) -> None:
         inflight = INFLIGHT
     shapes = [s for (_n, s, _sd) in items]
 
-    def make_batches(perm_cache: bool, n: int):
+    def make_batches(perm_cache: bool, n: int, cap: int = CLUSTER_CAP):
         sg = int(os.environ["QA_BENCH_STATS_GROUP"]) if "QA_BENCH_STATS_GROUP" in os.environ else None      # None: the batch's own choice
         bs = [GreedyBatch(shapes, **GREEDY, device=dev, perm_cache=perm_cache, stats_group=sg) for _ in range(n)]
-        if CLUSTER_CAP is not None and not cfg5:
+        if not cfg5:                                   # cfg5 keeps the batch's own choice for long lists (2-CTA clusters)
             for b in bs:
-                b.cluster_cap = CLUSTER_CAP
+                b.cluster_cap = cap
         for b in bs:
             b.load_device(host)
         torch.cuda.synchronize()
@@ -465,6 +470,15 @@ def bench_greedy(args, e) -> None:
     value = total_bytes * K / (ms * 1e-3) / 1e9
     ms_single = e.reduce_max(timed(batches, K, 1)) / K          # latency of one step with nothing else in flight
     results = batch.collect()
+    latency_schedule = None
+    if not cfg5 and CLUSTER_CAP != 0:                            # the same step alone with automatic cluster sizes
+        lb = make_batches(True, 1, cap=0)
+        ms_lat = e.reduce_max(timed(lb, K, 1)) / K
+        for r0, r1 in zip(results, lb[0].collect()):
+            assert (r0["assignment"] == r1["assignment"]).all() and r0["counts"] == r1["counts"]
+        latency_schedule = {"cluster_cap": "automatic (up to 16 CTAs per tensor)", "step_latency_ms": ms_lat,
+                            "note": "one step alone; with 12 lists in flight this schedule runs at 0.265 ms per step (profiles/r2_step_sweep3.txt)"}
+        del lb
     for b in batches[1:]:                                        # every in-flight list produced the same maps
         for r0, r1 in zip(results, b.collect()):
             assert (r0["assignment"] == r1["assignment"]).all() and r0["counts"] == r1["counts"]
@@ -662,7 +676,7 @@ def bench_greedy(args, e) -> None:
                 "e2e_plugin": e2e_plugin,
                 "gpu_launches": batch.launches_per_step * K,
                 "value_uncached": value_unc, "ms_per_step_uncached": ms_unc, "gpu_launches_uncached": launches_unc,
-                "step_latency_ms": ms_single,
+                "step_latency_ms": ms_single, "latency_schedule": latency_schedule,
                 "per_rank_ms_per_step": per_rank_ms,
                 "roofline": roofline, "roofline_by_kernel": [hbm, chain],
                 "pct_of_8TBs": 100.0 * value / world / 8000.0,
