@@ -267,7 +267,7 @@ def config_dict(cfg: str, n_gpus: int) -> dict:
                 "l2": "inputs_larger_than_l2 (374 MB per step vs 126 MB L2)", "parallelism": f"tensor-list x{n_gpus}",
                 "launch": "one CUDA graph per step for the device-resident value (kernels of all tensors on ~20 captured streams); "
                           "eager stream launches for e2e",
-                "inflight": f"{INFLIGHT} tensor lists in flight, each with its own buffers (the tile-stat passes of later steps overlap the greedy chains of earlier ones); "
+                "inflight": f"up to {INFLIGHT} tensor lists in flight (lists_in_flight: the count used, the largest that divides the timed steps), each with its own buffers (the tile-stat passes of later steps overlap the greedy chains of earlier ones); "
                             "step_latency_ms is one step alone",
                 "clusters": (f"chain clusters capped at {CLUSTER_CAP} CTAs per tensor (throughput schedule: a tensor's chain holds fewer SMs for longer); "
                              "latency_schedule = one step alone with automatic cluster sizes") if CLUSTER_CAP else "automatic cluster sizes (up to 16 CTAs per tensor)",
@@ -417,7 +417,12 @@ def bench_greedy(args, e) -> None:
     else:
         items = workload(rank)
         host = [synthetic.randn_bf16_cpu(shape, seed).pin_memory() for (_n, shape, seed) in items]
-        inflight = INFLIGHT
+        # lists in flight: every list runs its steps one after the other, so the K timed steps are spread evenly - the largest
+        # count up to INFLIGHT that divides K (20 steps: 10 lists x 2; 24: 12 x 2), unless QA_BENCH_INFLIGHT fixes it
+        inflight = min(INFLIGHT, K)
+        if "QA_BENCH_INFLIGHT" not in os.environ:
+            even = [n for n in range(inflight, 5, -1) if K % n == 0]
+            inflight = even[0] if even else inflight
     shapes = [s for (_n, s, _sd) in items]
 
     def make_batches(perm_cache: bool, n: int, cap: int = CLUSTER_CAP):
@@ -667,7 +672,7 @@ def bench_greedy(args, e) -> None:
     if rank == 0:
         line = {"metric": METRICS[args.config], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if cfg5 else "weak", "vs_baseline": None,
-                "dtype": "bf16 in; f32 group-scaled + f64 sums", "data": "synthetic", "config": config_dict(args.config, world),
+                "dtype": "bf16 in; f32 group-scaled + f64 sums", "data": "synthetic", "config": dict(config_dict(args.config, world), **({} if cfg5 else {"lists_in_flight": inflight})),
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": batch.d2h_bytes(),
                         "steps": Ke, "h2d_copy_gbs": h2d_alone[0], "h2d_copy_gbs_per_rank_alone": h2d_alone,
